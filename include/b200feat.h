@@ -1,0 +1,186 @@
+/*
+ * b200feat — C ABI of the B200-native (sm_100a) batched Kaldi-style feature extractor.
+ *
+ * This header is the drop-in boundary for the ONE hot path this repository replaces:
+ * lhotse's `FeatureExtractor.extract / extract_batch` for the Kaldi-compatible extractors
+ * (reference citations are relative to the lhotse tree, `/root/reference` in the build image):
+ *
+ *   - lhotse/features/base.py:37-222          FeatureExtractor ABC (extract, extract_batch)
+ *   - lhotse/features/kaldi/extractors.py:67  Fbank        (.extract :92, .extract_batch :117)
+ *   - lhotse/features/kaldi/extractors.py:201 Mfcc         (.extract :222, .extract_batch :244)
+ *   - lhotse/features/kaldi/extractors.py:297 Spectrogram  (.extract :318)
+ *   - lhotse/features/kaldi/extractors.py:407 LogSpectrogram (.extract :428)
+ *   - lhotse/features/kaldi/extractors.py:485 _extract_batch (pad, forward, trim)
+ *   - lhotse/features/kaldi/layers.py:151-186, :309-320, :392-402, :461-473, :565-578, :708-724
+ *     (the arithmetic), :727-772 (framing), lhotse/utils.py:424-434 (frame-count contract)
+ *
+ * The reference is pure Python and has no FFI for this path; the binding a maintainer adds is
+ * a `ctypes` stub inside a `FeatureExtractor` subclass — see INTEGRATION.md.  Everything here
+ * is plain C: pointers, sizes, status codes.  No torch types, no C++ exceptions cross it.
+ *
+ * Ownership: the caller owns every sample/output/meta buffer; a handle owns only its immutable
+ * constant tables (window, twiddles, sparse mel bank, DCT, lifter) on its device, plus — for
+ * the `*_host` entry point only — a grow-only pinned/device staging ring.
+ * Threading: a handle is immutable after create; `b200feat_extract` may be called concurrently
+ * from several host threads on different streams.  `b200feat_extract_host` serialises on the
+ * handle's staging ring.
+ * Errors: every entry returns 0 on success or a negative B200FEAT_E* code; the message is
+ * available from b200feat_last_error(handle) (or b200feat_global_error() when no handle exists).
+ */
+#ifndef B200FEAT_H_
+#define B200FEAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FEAT_ABI_VERSION 1
+
+/* status codes */
+#define B200FEAT_OK 0
+#define B200FEAT_EINVAL (-1)      /* bad argument / inconsistent plan */
+#define B200FEAT_EUNSUPPORTED (-2) /* plan not supported by any kernel */
+#define B200FEAT_ECUDA (-3)       /* CUDA runtime error (message has the cudaError string) */
+#define B200FEAT_ENODEVICE (-4)   /* no CUDA device / not an sm_100 part */
+#define B200FEAT_ESHORT (-5)      /* a cut is too short to be framed (reference raises too) */
+
+/* feature kinds — which reference module the plan mirrors */
+#define B200FEAT_FBANK 0           /* Wav2LogFilterBank, layers.py:476 */
+#define B200FEAT_MFCC 1            /* Wav2MFCC, layers.py:581 */
+#define B200FEAT_SPECTROGRAM 2     /* Wav2Spec, layers.py:336 */
+#define B200FEAT_LOG_SPECTROGRAM 3 /* Wav2LogSpec, layers.py:405 */
+
+/* sample dtypes accepted by the kernels */
+#define B200FEAT_F32 0 /* float32 in [-1, 1] — what lhotse hands to extract() */
+#define B200FEAT_I16 1 /* int16 PCM; converted as x/32768 on load (libsndfile convention) */
+
+/* output layouts */
+#define B200FEAT_OUT_PACKED 0 /* (sum_i T_i, F) rows of cut i start at row_off[i] */
+#define B200FEAT_OUT_PADDED 1 /* (B, T_max, F), rows >= T_i filled with pad_value
+                                 (= collate_matrices(padding_value=LOG_EPSILON), collation.py:506) */
+
+/* log-energy conventions (SURVEY.md §8a "semantic differences") */
+#define B200FEAT_ENERGY_LHOTSE 0 /* max(log(sum + 1e-15), log(floor)) iff floor > 0; layers.py:859-870 */
+#define B200FEAT_ENERGY_KALDI 1  /* max(log(max(sum, eps32)), log(floor)) iff floor != 0; torchaudio kaldi.py:116-122 */
+
+/* kernel selection (b200feat_plan_desc.kernel) */
+#define B200FEAT_KERNEL_AUTO 0
+#define B200FEAT_KERNEL_GENERIC 1 /* any L/S/N, mixed-radix Stockham in shared memory */
+#define B200FEAT_KERNEL_FAST 2    /* register-resident radix-16x16 rFFT, N = 512 */
+
+typedef struct b200feat_plan_desc {
+  int32_t struct_size;  /* sizeof(b200feat_plan_desc) — ABI guard */
+  int32_t feature;      /* B200FEAT_FBANK ... */
+  int32_t frame_length; /* L = floor(frame_length_s * sr), layers.py:114 */
+  int32_t frame_shift;  /* S = floor(frame_shift_s * sr), layers.py:116 */
+  int32_t fft_length;   /* N = next_pow2(L) or L, layers.py:264-265 */
+  int32_t num_filters;  /* M (mel bins); 0 for the spectrogram kinds */
+  int32_t num_ceps;     /* C (MFCC only) */
+  int32_t snip_edges;   /* layers.py:747-751 */
+  int32_t remove_dc_offset;
+  int32_t use_energy;   /* fbank: prepend; spectrograms: overwrite bin 0; mfcc: C0 */
+  int32_t raw_energy;   /* energy before (1) or after (0) pre-emphasis+window */
+  int32_t use_fft_mag;  /* |X| instead of |X|^2 */
+  int32_t energy_style; /* B200FEAT_ENERGY_* */
+  int32_t use_lifter;   /* multiply cepstra by lifter[] */
+  int32_t kernel;       /* B200FEAT_KERNEL_* */
+  int32_t reserved0;
+  float preemph_coeff;  /* 0 disables, layers.py:165 */
+  float energy_floor;   /* linear-domain floor (EPSILON = 1e-10 by default) */
+  float mel_floor;      /* clamp before log for fbank/mfcc: finfo(float32).eps, layers.py:572 */
+  float log_spec_eps;   /* additive eps of the log-spectrogram: 1e-15, layers.py:467 */
+} b200feat_plan_desc;
+
+typedef struct b200feat_handle b200feat_handle; /* opaque */
+
+typedef struct b200feat_stats {
+  int64_t calls;        /* extract launches since create */
+  int64_t cuts;         /* cuts processed */
+  int64_t frames;       /* feature rows produced */
+  int64_t samples;      /* input samples consumed */
+  int64_t kernel_launches; /* CUDA kernels launched by this handle */
+} b200feat_stats;
+
+/* Totals returned by b200feat_plan_batch. */
+typedef struct b200feat_batch_totals {
+  int64_t total_rows;    /* sum_i T_i (packed) */
+  int64_t max_frames;    /* T_max */
+  int64_t total_tiles;   /* work items of the selected kernel */
+  int64_t span_samples;  /* elements the sample buffer must hold (last offset + last length) */
+  int64_t out_floats;    /* floats the output buffer must hold for the chosen out_mode */
+} b200feat_batch_totals;
+
+int b200feat_version(void);
+const char *b200feat_global_error(void);
+
+/*
+ * Creates a handle on CUDA device `device`, uploading the constant tables.
+ *   window   : L floats                    (create_frame_window, layers.py:921-940)
+ *   mel_bank : K x M floats, row-major, K = N/2+1   (`_fb`, layers.py:541-563); NULL if M == 0
+ *   dct      : M x C floats, row-major     (`_dct`, layers.py:697-706); NULL unless MFCC
+ *   lifter   : C floats                    (`_lifter`, layers.py:681-695); NULL unless use_lifter
+ * Tables are taken from the caller so that they are bit-identical to the reference's
+ * float32 op sequence (and identical on every rank after an NCCL broadcast).
+ */
+int b200feat_create(const b200feat_plan_desc *desc, const float *window, const float *mel_bank,
+                    const float *dct, const float *lifter, int device, b200feat_handle **out);
+void b200feat_destroy(b200feat_handle *h);
+const char *b200feat_last_error(const b200feat_handle *h);
+
+/* T for a cut of n samples (layers.py:747-753); B200FEAT_ESHORT if it cannot be framed
+ * (n too short for a single reflection — the reference raises on those). */
+int64_t b200feat_num_frames(const b200feat_handle *h, int64_t num_samples);
+/* F: M (+1 with use_energy) for fbank, C for mfcc, N/2+1 for the spectrogram kinds. */
+int32_t b200feat_feature_dim(const b200feat_handle *h);
+/* B200FEAT_KERNEL_GENERIC or B200FEAT_KERNEL_FAST — what AUTO resolved to. */
+int32_t b200feat_kernel_kind(const b200feat_handle *h);
+/* number of int64 words of batch metadata for B cuts */
+int64_t b200feat_meta_words(int32_t batch);
+
+/*
+ * Host-side batch planning (pure integer work, no CUDA).
+ *   num_samples[B]     : length of every cut
+ *   sample_offsets[B]  : element offset of every cut in the sample buffer, or NULL to pack the
+ *                        cuts back to back with each start aligned to `align` elements
+ *   meta_host          : out, b200feat_meta_words(B) int64 words; copy verbatim to the device
+ * Layout of meta: [0,B) sample offsets | [B,2B) lengths | [2B,3B+1) row prefix | [3B+1,4B+2) tile prefix.
+ */
+int b200feat_plan_batch(const b200feat_handle *h, const int64_t *num_samples,
+                        const int64_t *sample_offsets, int32_t batch, int32_t align,
+                        int32_t out_mode, int64_t *meta_host, b200feat_batch_totals *totals);
+
+/*
+ * The hot call: device-resident ragged batch -> device-resident features.  Asynchronous on
+ * `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   samples_dev : float32 or int16 elements, addressed through meta's offsets
+ *   meta_dev    : device copy of meta_host
+ *   out_dev     : totals.out_floats floats, row-major (rows, F)
+ */
+int b200feat_extract(b200feat_handle *h, const void *samples_dev, int32_t sample_dtype,
+                     const int64_t *meta_dev, int32_t batch, const b200feat_batch_totals *totals,
+                     float *out_dev, int32_t out_mode, float pad_value, void *stream);
+
+/*
+ * Host-to-host convenience over the same kernels: what `FeatureExtractor.extract_batch` is for
+ * numpy inputs.  Stages the ragged batch through the handle's pinned ring, overlaps H2D /
+ * compute / D2H in chunks on internal streams, and blocks until `out_host` is complete.
+ *   samples_host : the cuts back to back (element offsets = running sum of num_samples)
+ *   out_host     : packed (sum T_i, F) or padded (B, T_max, F) floats
+ */
+int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t sample_dtype,
+                          const int64_t *num_samples, int32_t batch, float *out_host,
+                          int32_t out_mode, float pad_value);
+
+/* Read back a device-resident constant table (tests / NCCL-broadcast verification).
+ * which: 0 window, 1 dense mel bank reconstructed from the sparse form (K x M), 2 dct, 3 lifter,
+ * 4 twiddles (interleaved re,im). Returns the number of floats written or a negative code. */
+int64_t b200feat_get_table(b200feat_handle *h, int32_t which, float *out, int64_t capacity);
+
+int b200feat_get_stats(const b200feat_handle *h, b200feat_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FEAT_H_ */

@@ -1,0 +1,18 @@
+"""lhotse_b200 — B200-native (sm_100a) batched Kaldi-style feature extraction behind lhotse's
+``FeatureExtractor`` API.  See DESIGN.md for the hot-path scope and INTEGRATION.md for the binding."""
+from .plan import EPSILON, LOG_EPSILON, FeaturePlan, build_plan  # noqa: F401
+from .extractors import (  # noqa: F401
+    B200Fbank,
+    B200FbankConfig,
+    B200LogSpectrogram,
+    B200LogSpectrogramConfig,
+    B200Mfcc,
+    B200MfccConfig,
+    B200Spectrogram,
+    B200SpectrogramConfig,
+    from_reference_config,
+    install_as_default,
+)
+from .engine import Engine, B200FeatError, load_library  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,86 @@
+// Shared device/host definitions for the b200feat kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200feat.h"
+
+#define B200_MAX_STAGES 24
+
+// Constant tables + plan, passed to kernels by value (lives in constant bank / param space).
+struct DevPlan {
+  int feature, L, S, N, K, M, C, F;  // F = output row width
+  int Nc;                            // complex FFT length: N/2 (even N, packed real) or N (odd N)
+  int packed;                        // 1 if even N
+  int pad_left;                      // (L - S) / 2 when !snip_edges
+  int snip_edges, remove_dc, use_energy, raw_energy, use_mag, energy_style, use_lifter;
+  int nstages;
+  int radix[B200_MAX_STAGES];
+  float preemph, energy_floor_log, has_energy_floor, mel_floor, log_spec_eps;
+  const float *window;   // [L]
+  const float2 *tw;      // [Nc]   exp(-2 pi i k / Nc)
+  const float2 *tws;     // [N/2+1] exp(-2 pi i k / N) (packed split), even N only
+  const int *mel_start;  // [M] first FFT bin of filter m
+  const int *mel_len;    // [M] number of bins
+  const int *mel_woff;   // [M] offset into mel_w
+  const float *mel_w;    // [sum len]
+  const float *dct;      // [M*C]
+  const float *lifter;   // [C]
+};
+
+// One launch's view of the ragged batch (all device pointers).
+struct DevBatch {
+  const void *samples;
+  const int64_t *samp_off;  // [B] element offsets
+  const int64_t *nsamp;     // [B]
+  const int64_t *row_off;   // [B+1] packed-row prefix (absolute rows)
+  const int64_t *tile_off;  // [B+1] tile prefix (absolute)
+  float *out;
+  int64_t tile_base;    // first tile of this launch (absolute)
+  int64_t num_tiles;    // tiles in this launch
+  int64_t max_frames;   // T_max (padded mode)
+  int batch_first;      // absolute index of the first cut of this launch (padded mode row base)
+  int B;                // cuts in this launch
+  int out_mode;
+  float pad_value;
+};
+
+template <int DT>
+__device__ __forceinline__ float ld_sample(const void *base, int64_t i) {
+  if (DT == B200FEAT_I16) {
+    return (float)__ldg(reinterpret_cast<const int16_t *>(base) + i) * (1.0f / 32768.0f);
+  } else {
+    return __ldg(reinterpret_cast<const float *>(base) + i);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// index of the sample feeding (frame t, tap j): layers.py:753-772 in closed form
+__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
+  if (i < 0) i = -i - 1;
+  if (i >= n) i = 2 * n - 1 - i;
+  return i;
+}
+
+// largest b in [0, B) with prefix[b] <= g   (prefix has B+1 entries, prefix[0] <= g < prefix[B])
+__device__ __forceinline__ int find_segment(const int64_t *prefix, int B, int64_t g) {
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(prefix + mid) <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float log_energy_value(const DevPlan &p, float e) {
+  float le;
+  if (p.energy_style == B200FEAT_ENERGY_KALDI) le = logf(fmaxf(e, 1.1920929e-07f));
+  else le = logf(e + 1e-15f);
+  if (p.has_energy_floor != 0.0f) le = fmaxf(le, p.energy_floor_log);
+  return le;
+}

@@ -1,0 +1,214 @@
+// Generic fused kernel: any (L, S, N), any window, all four feature kinds.
+// One warp owns one frame at a time: gather(reflect) -> DC -> pre-emphasis -> window ->
+// mixed-radix Stockham FFT in shared memory (packed-real for even N) -> |X|^2 -> mel -> log
+// (-> DCT/lifter).  Replaces the op chain of lhotse/features/kaldi/layers.py:151-186 (Wav2Win),
+// :309-320 (rfft), :392-402 / :461-473 / :565-578 / :708-724 (spectrum epilogues) and the
+// framing of :727-772, with no HBM intermediates: 4*S bytes read, 4*F bytes written per frame.
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// One Stockham pass of radix R over a length-Nc complex sequence, executed by one warp.
+// out[(j / Ns) * Ns * R + (j % Ns) + q * Ns] = sum_r in[j + r * Nc / R] * W^(r * (k*Nc/(Ns*R) + q*Nc/R))
+__device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, float2 *__restrict__ dst,
+                                              const float2 *__restrict__ tw, int Nc, int R, int Ns,
+                                              int lane) {
+  const int nb = Nc / R;
+  const int tstep = Nc / (Ns * R);
+  if (R == 4) {
+    for (int j = lane; j < nb; j += 32) {
+      const int k = j % Ns;
+      float2 v0 = src[j], v1 = src[j + nb], v2 = src[j + 2 * nb], v3 = src[j + 3 * nb];
+      if (k != 0) {
+        const int ti = k * tstep;
+        v1 = cmul(v1, __ldg(tw + ti));
+        v2 = cmul(v2, __ldg(tw + 2 * ti));
+        v3 = cmul(v3, __ldg(tw + 3 * ti));
+      }
+      const float2 a = make_float2(v0.x + v2.x, v0.y + v2.y);
+      const float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
+      const float2 c = make_float2(v1.x + v3.x, v1.y + v3.y);
+      const float2 d = make_float2(v1.y - v3.y, v3.x - v1.x);  // -i * (v1 - v3)
+      const int o = (j / Ns) * Ns * 4 + k;
+      dst[o] = make_float2(a.x + c.x, a.y + c.y);
+      dst[o + Ns] = make_float2(b.x + d.x, b.y + d.y);
+      dst[o + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
+      dst[o + 3 * Ns] = make_float2(b.x - d.x, b.y - d.y);
+    }
+  } else if (R == 2) {
+    for (int j = lane; j < nb; j += 32) {
+      const int k = j % Ns;
+      float2 v0 = src[j], v1 = src[j + nb];
+      if (k != 0) v1 = cmul(v1, __ldg(tw + k * tstep));
+      const int o = (j / Ns) * Ns * 2 + k;
+      dst[o] = make_float2(v0.x + v1.x, v0.y + v1.y);
+      dst[o + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+    }
+  } else {
+    // arbitrary (prime) radix: O(R^2) direct DFT with exact table twiddles
+    const int qstep = Nc / R;
+    for (int j = lane; j < nb; j += 32) {
+      const int k = j % Ns;
+      const int o = (j / Ns) * Ns * R + k;
+      for (int q = 0; q < R; ++q) {
+        const int step = (k * tstep + q * qstep) % Nc;
+        float2 acc = src[j];
+        int ti = 0;
+        for (int r = 1; r < R; ++r) {
+          ti += step;
+          if (ti >= Nc) ti -= Nc;
+          const float2 w = __ldg(tw + ti);
+          const float2 v = src[j + r * nb];
+          acc.x += v.x * w.x - v.y * w.y;
+          acc.y += v.x * w.y + v.y * w.x;
+        }
+        dst[o + q * Ns] = acc;
+      }
+    }
+  }
+}
+
+// dynamic smem per warp (floats): raw[Nr] + 2 complex buffers of Nc
+__host__ __device__ inline int generic_raw_floats(int N) { return (N + 3) & ~3; }
+__host__ __device__ inline size_t generic_smem_per_warp(int N, int Nc) {
+  return (size_t)generic_raw_floats(N) * 4 + (size_t)Nc * 8 * 2;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, const DevBatch b) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  unsigned char *mine = smem_raw + (size_t)warp * generic_smem_per_warp(p.N, p.Nc);
+  float *raw = reinterpret_cast<float *>(mine);
+  float2 *bufA = reinterpret_cast<float2 *>(mine + (size_t)generic_raw_floats(p.N) * 4);
+  float2 *bufB = bufA + p.Nc;
+
+  // generic kernel: one tile == one output row
+  for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < b.num_tiles; g += (int64_t)gridDim.x * nwarps) {
+    const int64_t tile = b.tile_base + g;
+    int cut;
+    int64_t t, out_row;
+    if (b.out_mode == B200FEAT_OUT_PADDED) {
+      cut = (int)(g / b.max_frames);
+      t = g - (int64_t)cut * b.max_frames;
+      out_row = (int64_t)(b.batch_first + cut) * b.max_frames + t;
+    } else {
+      cut = find_segment(b.row_off, b.B, tile);
+      t = tile - __ldg(b.row_off + cut);
+      out_row = tile;
+    }
+    float *out = b.out + out_row * p.F;
+    const int64_t T = __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut);
+    if (t >= T) {  // padded tail
+      for (int c = lane; c < p.F; c += 32) out[c] = b.pad_value;
+      continue;
+    }
+    const int64_t n = __ldg(b.nsamp + cut);
+    const int64_t xoff = __ldg(b.samp_off + cut);
+    const int64_t base = t * p.S - (p.snip_edges ? 0 : p.pad_left);
+
+    // ---- gather + mean (layers.py:753-772, :155-157)
+    float s = 0.f;
+    for (int j = lane; j < p.L; j += 32) {
+      int64_t i = base + j;
+      if (!p.snip_edges) i = reflect_index(i, n);
+      const float v = ld_sample<DT>(b.samples, xoff + i);
+      raw[j] = v;
+      s += v;
+    }
+    s = warp_sum(s);
+    const float mu = p.remove_dc ? s / (float)p.L : 0.f;
+    __syncwarp();
+
+    // ---- energy, pre-emphasis, window, zero-pad (layers.py:159-181)
+    float e = 0.f;
+    float *ybuf = reinterpret_cast<float *>(bufA);
+    for (int j = lane; j < p.N; j += 32) {
+      float y = 0.f;
+      if (j < p.L) {
+        const float d = raw[j] - mu;
+        if (p.raw_energy) e += d * d;
+        float g0 = d;
+        if (p.preemph != 0.f) {
+          const float dp = raw[j > 0 ? j - 1 : 0] - mu;
+          g0 = __fsub_rn(d, __fmul_rn(p.preemph, dp));
+        }
+        y = g0 * __ldg(p.window + j);
+        if (!p.raw_energy) e += y * y;
+      }
+      if (p.packed) ybuf[j] = y; else bufA[j] = make_float2(y, 0.f);
+    }
+    float le = 0.f;
+    if (p.use_energy) le = log_energy_value(p, warp_sum(e));
+    __syncwarp();
+
+    // ---- FFT (layers.py:32-36)
+    float2 *src = bufA, *dst = bufB;
+    int Ns = 1;
+    for (int st = 0; st < p.nstages; ++st) {
+      const int R = p.radix[st];
+      stockham_pass(src, dst, p.tw, p.Nc, R, Ns, lane);
+      __syncwarp();
+      float2 *tmp = src; src = dst; dst = tmp;
+      Ns *= R;
+    }
+
+    // ---- spectrum (layers.py:38-42) into raw[0..K)
+    for (int k = lane; k < p.K; k += 32) {
+      float xr, xi;
+      if (p.packed) {
+        const float2 zk = src[k == p.Nc ? 0 : k];
+        const float2 zc = src[k == 0 ? 0 : p.Nc - k];  // partner (to be conjugated)
+        const float er = zk.x + zc.x, ei = zk.y - zc.y;
+        const float orr = zk.x - zc.x, oi = zk.y + zc.y;
+        const float2 w = __ldg(p.tws + k);
+        const float tr = w.x * orr - w.y * oi, ti = w.x * oi + w.y * orr;
+        xr = 0.5f * (er + ti);
+        xi = 0.5f * (ei - tr);
+      } else {
+        const float2 z = src[k];
+        xr = z.x; xi = z.y;
+      }
+      const float pw = xr * xr + xi * xi;
+      raw[k] = p.use_mag ? sqrtf(pw) : pw;
+    }
+    __syncwarp();
+
+    // ---- epilogue
+    if (p.feature == B200FEAT_SPECTROGRAM) {
+      for (int k = lane; k < p.K; k += 32) out[k] = (k == 0 && p.use_energy) ? le : raw[k];
+    } else if (p.feature == B200FEAT_LOG_SPECTROGRAM) {
+      for (int k = lane; k < p.K; k += 32)
+        out[k] = (k == 0 && p.use_energy) ? le : logf(raw[k] + p.log_spec_eps);
+    } else {
+      float *mlog = reinterpret_cast<float *>(dst);  // scratch (FFT buffer not holding the result)
+      const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      for (int m = lane; m < p.M; m += 32) {
+        const int st = __ldg(p.mel_start + m), len = __ldg(p.mel_len + m);
+        const float *w = p.mel_w + __ldg(p.mel_woff + m);
+        float acc = 0.f;
+        for (int i = 0; i < len; ++i) acc += raw[st + i] * __ldg(w + i);
+        const float v = logf(fmaxf(acc, p.mel_floor));
+        if (p.feature == B200FEAT_FBANK) out[m + shift] = v; else mlog[m] = v;
+      }
+      if (p.feature == B200FEAT_FBANK) {
+        if (shift && lane == 0) out[0] = le;
+      } else {
+        __syncwarp();
+        for (int c = lane; c < p.C; c += 32) {
+          float acc = 0.f;
+          for (int m = 0; m < p.M; ++m) acc += mlog[m] * __ldg(p.dct + m * p.C + c);
+          if (p.use_lifter) acc *= __ldg(p.lifter + c);
+          if (p.use_energy && c == 0) acc = le;
+          out[c] = acc;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}

@@ -1,0 +1,285 @@
+"""
+ctypes binding of ``libb200feat.so`` (include/b200feat.h) + the host-side staging of ragged
+batches.  torch is used here for device memory, pinned memory and streams only.
+
+There is NO CPU fallback: if the library is missing, or no sm_100 GPU is visible, creating an
+``Engine`` raises.  (The CPU oracle under ``oracle/`` is test infrastructure and is never
+imported from this package.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from .plan import FEATURE_KINDS, FeaturePlan
+
+LIB_NAME = "libb200feat.so"
+_LIB = None
+_LIB_LOCK = threading.Lock()
+
+OUT_PACKED, OUT_PADDED = 0, 1
+DT_F32, DT_I16 = 0, 1
+KERNELS = {"auto": 0, "generic": 1, "fast": 2}
+KERNEL_NAMES = {1: "generic", 2: "fast"}
+
+
+class B200FeatError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200feat error {code}: {msg}")
+        self.code = code
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("feature", C.c_int32), ("frame_length", C.c_int32),
+        ("frame_shift", C.c_int32), ("fft_length", C.c_int32), ("num_filters", C.c_int32),
+        ("num_ceps", C.c_int32), ("snip_edges", C.c_int32), ("remove_dc_offset", C.c_int32),
+        ("use_energy", C.c_int32), ("raw_energy", C.c_int32), ("use_fft_mag", C.c_int32),
+        ("energy_style", C.c_int32), ("use_lifter", C.c_int32), ("kernel", C.c_int32),
+        ("reserved0", C.c_int32), ("preemph_coeff", C.c_float), ("energy_floor", C.c_float),
+        ("mel_floor", C.c_float), ("log_spec_eps", C.c_float),
+    ]
+
+
+class BatchTotals(C.Structure):
+    _fields_ = [("total_rows", C.c_int64), ("max_frames", C.c_int64), ("total_tiles", C.c_int64),
+                ("span_samples", C.c_int64), ("out_floats", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("calls", C.c_int64), ("cuts", C.c_int64), ("frames", C.c_int64),
+                ("samples", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+EXPORTS = [
+    "b200feat_version", "b200feat_global_error", "b200feat_create", "b200feat_destroy",
+    "b200feat_last_error", "b200feat_num_frames", "b200feat_feature_dim", "b200feat_kernel_kind",
+    "b200feat_meta_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
+    "b200feat_get_table", "b200feat_get_stats",
+]
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+
+def load_library():
+    """Loads the in-tree CUDA library; raises (never falls back) when it is absent."""
+    global _LIB
+    with _LIB_LOCK:
+        if _LIB is not None:
+            return _LIB
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing: build it with `python -m lhotse_b200.build` (needs nvcc). "
+                "lhotse_b200 has no CPU fallback."
+            )
+        lib = C.CDLL(path)
+        vp, i32, i64, fp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
+        i64p = C.POINTER(C.c_int64)
+        lib.b200feat_version.restype = C.c_int
+        lib.b200feat_global_error.restype = C.c_char_p
+        lib.b200feat_create.restype = C.c_int
+        lib.b200feat_create.argtypes = [C.POINTER(PlanDesc), vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+        lib.b200feat_destroy.restype = None
+        lib.b200feat_destroy.argtypes = [vp]
+        lib.b200feat_last_error.restype = C.c_char_p
+        lib.b200feat_last_error.argtypes = [vp]
+        lib.b200feat_num_frames.restype = i64
+        lib.b200feat_num_frames.argtypes = [vp, i64]
+        lib.b200feat_feature_dim.restype = i32
+        lib.b200feat_feature_dim.argtypes = [vp]
+        lib.b200feat_kernel_kind.restype = i32
+        lib.b200feat_kernel_kind.argtypes = [vp]
+        lib.b200feat_meta_words.restype = i64
+        lib.b200feat_meta_words.argtypes = [i32]
+        lib.b200feat_plan_batch.restype = C.c_int
+        lib.b200feat_plan_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, C.POINTER(BatchTotals)]
+        lib.b200feat_extract.restype = C.c_int
+        lib.b200feat_extract.argtypes = [vp, vp, i32, vp, i32, C.POINTER(BatchTotals), vp, i32, C.c_float, vp]
+        lib.b200feat_extract_host.restype = C.c_int
+        lib.b200feat_extract_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.c_float]
+        lib.b200feat_get_table.restype = i64
+        lib.b200feat_get_table.argtypes = [vp, i32, vp, i64]
+        lib.b200feat_get_stats.restype = C.c_int
+        lib.b200feat_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        if lib.b200feat_version() != 1:
+            raise ImportError("libb200feat.so ABI version mismatch")
+        _LIB = lib
+        return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One handle = one (plan, device).  Thread-safe for `extract_device` on distinct streams."""
+
+    def __init__(self, plan: FeaturePlan, device: Union[int, str, torch.device] = 0, kernel: str = "auto"):
+        self.lib = load_library()
+        self.plan = plan
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise ValueError(f"lhotse_b200 extractors run on CUDA devices only, got {dev}")
+        self.device_index = dev.index if dev.index is not None else (
+            torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.device = torch.device("cuda", self.device_index)
+        d = PlanDesc()
+        d.struct_size = C.sizeof(PlanDesc)
+        d.feature = FEATURE_KINDS[plan.feature]
+        d.frame_length, d.frame_shift, d.fft_length = plan.L, plan.S, plan.N
+        d.num_filters, d.num_ceps = plan.num_filters, plan.num_ceps
+        d.snip_edges, d.remove_dc_offset = int(plan.snip_edges), int(plan.remove_dc_offset)
+        d.use_energy, d.raw_energy, d.use_fft_mag = int(plan.use_energy), int(plan.raw_energy), int(plan.use_fft_mag)
+        d.energy_style = plan.energy_style
+        d.use_lifter = int(plan.lifter is not None)
+        d.kernel = KERNELS[kernel]
+        d.preemph_coeff, d.energy_floor = plan.preemph_coeff, plan.energy_floor
+        d.mel_floor, d.log_spec_eps = plan.mel_floor, plan.log_spec_eps
+        tabs = [None if t is None else np.ascontiguousarray(t, dtype=np.float32)
+                for t in (plan.window, plan.mel_bank, plan.dct, plan.lifter)]
+        h = C.c_void_p()
+        rc = self.lib.b200feat_create(C.byref(d), _ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]), _ptr(tabs[3]),
+                                      self.device_index, C.byref(h))
+        if rc != 0:
+            raise B200FeatError(rc, self.lib.b200feat_global_error().decode())
+        self._h = h
+        self.feature_dim = int(self.lib.b200feat_feature_dim(h))
+        self.kernel = KERNEL_NAMES[int(self.lib.b200feat_kernel_kind(h))]
+        self._pinned_meta = {}  # per-thread pinned meta staging
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b200feat_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise B200FeatError(rc, self.lib.b200feat_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ integer contract
+    def num_frames(self, num_samples: int) -> int:
+        t = int(self.lib.b200feat_num_frames(self._h, int(num_samples)))
+        if t < 0:
+            raise ValueError(
+                f"a cut of {num_samples} samples cannot be framed with L={self.plan.L}, S={self.plan.S} "
+                "(too short for reflect padding) — the reference raises on such inputs as well")
+        return t
+
+    def plan_batch(self, num_samples: Sequence[int], offsets: Optional[Sequence[int]] = None,
+                   align: int = 4, out_mode: int = OUT_PACKED) -> Tuple[np.ndarray, BatchTotals]:
+        B = len(num_samples)
+        ns = np.ascontiguousarray(num_samples, dtype=np.int64)
+        off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        meta = np.empty(int(self.lib.b200feat_meta_words(B)), dtype=np.int64)
+        tot = BatchTotals()
+        rc = self.lib.b200feat_plan_batch(self._h, _ptr(ns), _ptr(off), B, align, out_mode, _ptr(meta), C.byref(tot))
+        if rc == -5:
+            raise ValueError(self.lib.b200feat_last_error(self._h).decode())
+        self._check(rc)
+        return meta, tot
+
+    # ------------------------------------------------------------------ device-resident path
+    def extract_device(self, samples: torch.Tensor, num_samples: Sequence[int],
+                       offsets: Optional[Sequence[int]] = None, out_mode: int = OUT_PACKED,
+                       pad_value: float = 0.0, out: Optional[torch.Tensor] = None,
+                       meta_dev: Optional[torch.Tensor] = None, totals: Optional[BatchTotals] = None,
+                       ) -> Tuple[torch.Tensor, np.ndarray]:
+        """samples: 1-D CUDA tensor (float32 or int16) holding the cuts at `offsets` (element units;
+        default: back to back with 4-element alignment — see `pack_device`).
+        Returns (features, row_prefix): packed (sum T, F) or padded (B, Tmax, F)."""
+        assert samples.is_cuda and samples.dim() == 1 and samples.is_contiguous()
+        dt = {torch.float32: DT_F32, torch.int16: DT_I16}[samples.dtype]
+        B = len(num_samples)
+        if meta_dev is None or totals is None:
+            meta, totals = self.plan_batch(num_samples, offsets, out_mode=out_mode)
+            assert totals.span_samples <= samples.numel(), "sample buffer shorter than offsets + lengths"
+            meta_dev = torch.from_numpy(meta).to(samples.device, non_blocking=False)
+            row_prefix = meta[2 * B: 3 * B + 1]
+        else:
+            row_prefix = None
+        if out is None:
+            shape = (B, totals.max_frames, self.feature_dim) if out_mode == OUT_PADDED else (totals.total_rows, self.feature_dim)
+            out = torch.empty(shape, dtype=torch.float32, device=samples.device)
+        else:
+            assert out.is_cuda and out.is_contiguous() and out.numel() >= totals.out_floats
+        stream = torch.cuda.current_stream(samples.device).cuda_stream
+        self._check(self.lib.b200feat_extract(self._h, samples.data_ptr(), dt, meta_dev.data_ptr(), B,
+                                              C.byref(totals), out.data_ptr(), out_mode, float(pad_value), stream))
+        return out, row_prefix
+
+    # ------------------------------------------------------------------ host-to-host path
+    def extract_host(self, samples: Union[np.ndarray, torch.Tensor], num_samples: Sequence[int],
+                     out_mode: int = OUT_PACKED, pad_value: float = 0.0,
+                     out: Optional[Union[np.ndarray, torch.Tensor]] = None):
+        """samples: the cuts back to back in ONE host buffer (numpy or CPU torch tensor, float32 or
+        int16; pinned memory makes the H2D copies asynchronous).  Blocks until `out` is filled."""
+        if isinstance(samples, torch.Tensor):
+            assert not samples.is_cuda and samples.is_contiguous()
+            dt = {torch.float32: DT_F32, torch.int16: DT_I16}[samples.dtype]
+            sptr, numel = samples.data_ptr(), samples.numel()
+        else:
+            samples = np.ascontiguousarray(samples)
+            dt = {np.dtype(np.float32): DT_F32, np.dtype(np.int16): DT_I16}[samples.dtype]
+            sptr, numel = samples.ctypes.data, samples.size
+        ns = np.ascontiguousarray(num_samples, dtype=np.int64)
+        assert int(ns.sum()) <= numel
+        B = len(ns)
+        Ts = [self.num_frames(int(n)) for n in ns]
+        rows = B * max(Ts) if out_mode == OUT_PADDED else sum(Ts)
+        shape = (B, max(Ts), self.feature_dim) if out_mode == OUT_PADDED else (rows, self.feature_dim)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        optr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+        self._check(self.lib.b200feat_extract_host(self._h, sptr, dt, _ptr(ns), B, optr, out_mode, float(pad_value)))
+        return out, np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
+
+    # ------------------------------------------------------------------ introspection
+    def get_table(self, which: int) -> np.ndarray:
+        cap = max(self.plan.K * max(self.plan.num_filters, 1), self.plan.N * 2, 8192)
+        buf = np.empty(cap, dtype=np.float32)
+        n = int(self.lib.b200feat_get_table(self._h, which, _ptr(buf), cap))
+        if n < 0:
+            self._check(n)
+        return buf[:n].copy()
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.b200feat_get_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+
+def pack_device(tensors: List[torch.Tensor], device: torch.device, align: int = 4,
+                dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, List[int], List[int]]:
+    """Packs 1-D waveforms into one ragged device buffer (each start aligned to `align` elements).
+    Host tensors go through ONE pinned staging buffer and ONE H2D copy; device tensors are copied
+    device-to-device."""
+    lens = [int(t.numel()) for t in tensors]
+    offs, cur = [], 0
+    for n in lens:
+        cur = (cur + align - 1) // align * align
+        offs.append(cur)
+        cur += n
+    total = cur
+    if all(not t.is_cuda for t in tensors):
+        stage = torch.empty(total, dtype=dtype, pin_memory=torch.cuda.is_available())
+        for t, o, n in zip(tensors, offs, lens):
+            stage[o:o + n].copy_(t.reshape(-1))
+        return stage.to(device, non_blocking=True), lens, offs
+    buf = torch.empty(total, dtype=dtype, device=device)
+    for t, o, n in zip(tensors, offs, lens):
+        buf[o:o + n].copy_(t.reshape(-1), non_blocking=True)
+    return buf, lens, offs

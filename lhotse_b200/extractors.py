@@ -1,0 +1,392 @@
+"""
+B200-native counterparts of lhotse's Kaldi-family extractors, behind the unchanged
+``FeatureExtractor`` API (lhotse/features/base.py:37-222):
+
+    reference class (lhotse/features/kaldi/extractors.py)      here
+    ---------------------------------------------------------------------------
+    Fbank           :67   name "kaldi-fbank"                   B200Fbank           "b200-fbank"
+    Mfcc            :201  name "kaldi-mfcc"                    B200Mfcc            "b200-mfcc"
+    Spectrogram     :297  name "kaldi-spectrogram"             B200Spectrogram     "b200-spectrogram"
+    LogSpectrogram  :407  name "kaldi-log-spectrogram"         B200LogSpectrogram  "b200-log-spectrogram"
+
+Same config fields, same container rules for ``extract`` / ``extract_batch``
+(extractors.py:92-132, :485-554), same ``mix`` / ``compute_energy`` / ``scale`` statics.
+Deliberate differences, all documented in DESIGN.md:
+  * ``extract_batch`` frames every cut on its own (ragged), so each item equals ``extract`` on that
+    item; the reference zero-pads to the longest item and reflects at the *padded* end, which
+    perturbs the last 1-2 frames of every shorter item.
+  * ``dither != 0`` is rejected (the reference uses the global torch RNG, layers.py:190-193).
+  * ``device`` must be a CUDA device; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import warnings
+from dataclasses import asdict, dataclass
+from typing import Any, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .base import FeatureExtractor, register_extractor
+from .engine import OUT_PACKED, OUT_PADDED, Engine, pack_device
+from .plan import EPSILON, LOG_EPSILON, FeaturePlan, build_plan
+
+Seconds = float
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+def _asdict_nonull(dclass) -> Dict[str, Any]:
+    return {k: v for k, v in asdict(dclass).items() if v is not None}  # lhotse/utils.py asdict_nonull
+
+
+class _ConfigMixin:
+    def __post_init__(self):
+        if getattr(self, "num_mel_bins", None) is not None:  # extractors.py:46-51
+            self.num_filters = self.num_mel_bins
+            self.num_mel_bins = None
+        if self.snip_edges:
+            warnings.warn(
+                "`snip_edges` is set to True, which may cause issues in duration to num-frames conversion in Lhotse."
+            )
+
+    def to_dict(self) -> Dict[str, Any]:
+        return _asdict_nonull(self)
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any]):
+        return cls(**data)
+
+
+@dataclass
+class B200FbankConfig(_ConfigMixin):
+    """Field-for-field FbankConfig (extractors.py:24-44) with `device="cuda"` and a `kernel` knob."""
+
+    sampling_rate: int = 16000
+    frame_length: Seconds = 0.025
+    frame_shift: Seconds = 0.01
+    round_to_power_of_two: bool = True
+    remove_dc_offset: bool = True
+    preemph_coeff: float = 0.97
+    window_type: str = "povey"
+    dither: float = 0.0
+    snip_edges: bool = False
+    energy_floor: float = EPSILON
+    raw_energy: bool = True
+    use_energy: bool = False
+    use_fft_mag: bool = False
+    low_freq: float = 20.0
+    high_freq: float = -400.0
+    num_filters: int = 80
+    num_mel_bins: Optional[int] = None  # do not use
+    norm_filters: bool = False
+    torchaudio_compatible_mel_scale: bool = True
+    device: str = "cuda"
+    kernel: str = "auto"  # auto | fast | generic
+
+
+@dataclass
+class B200MfccConfig(_ConfigMixin):
+    """Field-for-field MfccConfig (extractors.py:156-178)."""
+
+    sampling_rate: int = 16000
+    frame_length: Seconds = 0.025
+    frame_shift: Seconds = 0.01
+    round_to_power_of_two: bool = True
+    remove_dc_offset: bool = True
+    preemph_coeff: float = 0.97
+    window_type: str = "povey"
+    dither: float = 0.0
+    snip_edges: bool = False
+    energy_floor: float = EPSILON
+    raw_energy: bool = True
+    use_energy: bool = False
+    use_fft_mag: bool = False
+    low_freq: float = 20.0
+    high_freq: float = -400.0
+    num_filters: int = 23
+    torchaudio_compatible_mel_scale: bool = True
+    num_mel_bins: Optional[int] = None  # do not use
+    norm_filters: bool = False
+    num_ceps: int = 13
+    cepstral_lifter: int = 22
+    device: str = "cuda"
+    kernel: str = "auto"
+
+
+@dataclass
+class B200SpectrogramConfig(_ConfigMixin):
+    """Field-for-field SpectrogramConfig (extractors.py:266-281)."""
+
+    sampling_rate: int = 16000
+    frame_length: Seconds = 0.025
+    frame_shift: Seconds = 0.01
+    round_to_power_of_two: bool = True
+    remove_dc_offset: bool = True
+    preemph_coeff: float = 0.97
+    window_type: str = "povey"
+    dither: float = 0.0
+    snip_edges: bool = False
+    energy_floor: float = EPSILON
+    raw_energy: bool = True
+    use_energy: bool = False
+    use_fft_mag: bool = False
+    device: str = "cuda"
+    kernel: str = "auto"
+
+
+@dataclass
+class B200LogSpectrogramConfig(B200SpectrogramConfig):
+    """Field-for-field LogSpectrogramConfig (extractors.py:376-391)."""
+
+
+def _first_channel_1d(x: ArrayLike) -> ArrayLike:
+    """(n,) stays; (C, n) -> channel 0 (extractors.py:107-110 keeps `[0]` of the module output)."""
+    if x.ndim == 1:
+        return x
+    if x.ndim == 2:
+        return x[0]
+    raise ValueError(f"expected a (n,) or (C, n) waveform, got shape {tuple(x.shape)}")
+
+
+class _B200Extractor(FeatureExtractor):
+    feature_kind: str = None
+    _returns_cpu_tensor = False  # Spectrogram/LogSpectrogram `.cpu()` their tensor outputs (:343, :453)
+
+    def __init__(self, config: Optional[Any] = None):
+        super().__init__(config=config)
+        self._engine: Optional[Engine] = None
+        self._plan: Optional[FeaturePlan] = None
+        self.plan  # validate the config eagerly (no CUDA needed)
+
+    # -- lazy CUDA state (fork/spawn/pickle friendly: set.py:2166 pickles the extractor) ---------
+    @property
+    def plan(self) -> FeaturePlan:
+        if self._plan is None:
+            self._plan = build_plan(self.feature_kind, self.config)
+        return self._plan
+
+    @property
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self.plan, device=self.config.device, kernel=getattr(self.config, "kernel", "auto"))
+        return self._engine
+
+    def __getstate__(self):
+        return {"config": self.config}
+
+    def __setstate__(self, state):
+        self.config = state["config"]
+        self._engine = None
+        self._plan = None
+
+    # -- FeatureExtractor protocol --------------------------------------------------------------
+    @property
+    def device(self) -> Union[str, torch.device]:
+        return self.config.device
+
+    def to(self, device: str):
+        self.config.device = str(device)
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    @property
+    def frame_shift(self) -> Seconds:
+        return self.config.frame_shift
+
+    def _check_sr(self, sampling_rate: int):
+        assert sampling_rate == self.config.sampling_rate, (
+            f"{type(self).__name__} was instantiated for sampling_rate "
+            f"{self.config.sampling_rate}, but "
+            f"sampling_rate={sampling_rate} was passed to extract(). "
+            "Note you can use CutSet/RecordingSet.resample() to change the audio sampling rate."
+        )
+
+    def extract(self, samples: ArrayLike, sampling_rate: int) -> ArrayLike:
+        self._check_sr(sampling_rate)
+        is_numpy = not isinstance(samples, torch.Tensor)
+        x = _first_channel_1d(samples)
+        if is_numpy:
+            x = np.ascontiguousarray(x)
+            if x.dtype not in (np.float32, np.int16):
+                x = x.astype(np.float32)
+            feats, _ = self.engine.extract_host(x, [x.shape[0]])
+            return feats
+        x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.int16):
+            x = x.to(torch.float32)
+        dev = self.engine.device
+        xd = x.to(dev, non_blocking=True)
+        feats, _ = self.engine.extract_device(xd, [xd.numel()], offsets=[0])
+        return feats.cpu() if self._returns_cpu_tensor else feats
+
+    def extract_batch(
+        self,
+        samples: Union[ArrayLike, Sequence[np.ndarray], Sequence[torch.Tensor]],
+        sampling_rate: int,
+        lengths: Optional[ArrayLike] = None,
+    ) -> Union[ArrayLike, List[np.ndarray], List[torch.Tensor]]:
+        """Container rules of `_extract_batch` (extractors.py:485-554)."""
+        self._check_sr(sampling_rate)
+        eng = self.engine
+        input_is_list = False
+        if lengths is not None:
+            assert isinstance(
+                samples, torch.Tensor
+            ), "If `lengths` is provided, `samples` must be a batched and padded torch.Tensor."
+            assert samples.dim() == 2
+            lens = [int(l) for l in lengths]
+            B, nmax = samples.shape
+            assert len(lens) == B and max(lens) <= nmax
+            buf = samples.contiguous()
+            if buf.dtype not in (torch.float32, torch.int16):
+                buf = buf.to(torch.float32)
+            buf = buf.to(eng.device, non_blocking=True).reshape(-1)
+            out, prefix = eng.extract_device(buf, lens, offsets=[i * nmax for i in range(B)])
+            result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
+            input_is_torch = True
+        else:
+            if isinstance(samples, (list, tuple)):
+                input_is_list = True
+                items = list(samples)
+            elif samples.ndim > 1:
+                items = list(samples)
+            else:
+                items = [samples.reshape(1, -1)]
+            input_is_torch = any(isinstance(x, torch.Tensor) for x in items)
+            if input_is_torch:
+                flat = [(torch.from_numpy(x) if isinstance(x, np.ndarray) else x).squeeze() for x in items]
+                dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
+                buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
+                out, prefix = eng.extract_device(buf, lens, offsets=offs)
+            else:
+                flat = [np.asarray(x).squeeze() for x in items]
+                dt = np.int16 if all(a.dtype == np.int16 for a in flat) else np.float32
+                lens = [int(a.shape[0]) for a in flat]
+                stage = torch.empty(sum(lens), dtype=torch.int16 if dt == np.int16 else torch.float32,
+                                    pin_memory=torch.cuda.is_available())
+                view, o = stage.numpy(), 0
+                for a, n in zip(flat, lens):
+                    view[o:o + n] = a
+                    o += n
+                out, prefix = eng.extract_host(stage, lens)
+            result = [out[prefix[i]: prefix[i + 1]] for i in range(len(lens))]
+        if self._returns_cpu_tensor and input_is_torch:
+            result = [r.cpu() for r in result]
+
+        # If all items are of the same shape, stack (a view of the packed buffer: no copy)
+        if len(result) == 1:
+            return result if input_is_list else result[0]
+        if all(item.shape == result[0].shape for item in result[1:]):
+            if self._returns_cpu_tensor and input_is_torch:
+                return torch.stack(result, dim=0)
+            return out.reshape(len(result), result[0].shape[0], result[0].shape[1])
+        return result
+
+    # -- extras used by the fused-collation ("next") path -----------------------
+    def extract_batch_padded(self, samples: Sequence[torch.Tensor], sampling_rate: int,
+                             padding_value: float = LOG_EPSILON):
+        """Ragged list -> ((B, T_max, F) padded with `padding_value`, int64 frame lengths), i.e.
+        `extract_batch` + `collate_matrices(padding_value=LOG_EPSILON)` (collation.py:506-533,
+        input_strategies.py:441-462) in one launch, staying on the device."""
+        self._check_sr(sampling_rate)
+        eng = self.engine
+        flat = [(torch.from_numpy(x) if isinstance(x, np.ndarray) else x).squeeze() for x in samples]
+        buf, lens, offs = pack_device(flat, eng.device)
+        out, prefix = eng.extract_device(buf, lens, offsets=offs, out_mode=OUT_PADDED, pad_value=padding_value)
+        feat_lens = torch.from_numpy(np.diff(prefix)).to(torch.int64)
+        return out, feat_lens
+
+
+@register_extractor
+class B200Fbank(_B200Extractor):
+    name = "b200-fbank"
+    config_type = B200FbankConfig
+    feature_kind = "fbank"
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self.config.num_filters  # extractors.py:89-90 (ignores use_energy, as the reference does)
+
+    @staticmethod
+    def mix(features_a: np.ndarray, features_b: np.ndarray, energy_scaling_factor_b: float) -> np.ndarray:
+        return np.log(np.maximum(EPSILON, np.exp(features_a) + energy_scaling_factor_b * np.exp(features_b)))
+
+    @staticmethod
+    def compute_energy(features: np.ndarray) -> float:
+        return float(np.sum(np.exp(features)))
+
+    @staticmethod
+    def scale(features: np.ndarray, energy_scaling_factor: float) -> np.ndarray:
+        return features + np.log(energy_scaling_factor)
+
+
+@register_extractor
+class B200Mfcc(_B200Extractor):
+    name = "b200-mfcc"
+    config_type = B200MfccConfig
+    feature_kind = "mfcc"
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self.config.num_ceps
+
+
+@register_extractor
+class B200Spectrogram(_B200Extractor):
+    name = "b200-spectrogram"
+    config_type = B200SpectrogramConfig
+    feature_kind = "spectrogram"
+    _returns_cpu_tensor = True
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self.plan.N // 2 + 1
+
+    @staticmethod
+    def mix(features_a: np.ndarray, features_b: np.ndarray, energy_scaling_factor_b: float) -> np.ndarray:
+        return features_a + energy_scaling_factor_b * features_b
+
+    @staticmethod
+    def compute_energy(features: np.ndarray) -> float:
+        return float(np.sum(features))
+
+    @staticmethod
+    def scale(features: np.ndarray, energy_scaling_factor: float) -> np.ndarray:
+        return energy_scaling_factor * features
+
+
+@register_extractor
+class B200LogSpectrogram(B200Spectrogram):
+    name = "b200-log-spectrogram"
+    config_type = B200LogSpectrogramConfig
+    feature_kind = "log-spectrogram"
+
+
+_ALIASES = {
+    "kaldi-fbank": B200Fbank, "kaldi-mfcc": B200Mfcc,
+    "kaldi-spectrogram": B200Spectrogram, "kaldi-log-spectrogram": B200LogSpectrogram,
+}
+
+
+def install_as_default() -> None:
+    """Re-points lhotse's registry names ("kaldi-fbank", ...) at the B200 classes, so existing
+    YAML configs and `Features.type` values in manifests (resolved by
+    `create_default_feature_extractor`, base.py:381, used by MixedCut.load_features mixed.py:1252)
+    pick the GPU implementation without editing them."""
+    from .base import _REGISTRY
+
+    for name, cls in _ALIASES.items():
+        _REGISTRY[name] = cls
+
+
+def from_reference_config(cfg: Any, device: str = "cuda"):
+    """Builds the matching B200 extractor from a lhotse FbankConfig/MfccConfig/SpectrogramConfig/
+    LogSpectrogramConfig instance (field names are identical)."""
+    kind = type(cfg).__name__
+    table = {"FbankConfig": (B200Fbank, B200FbankConfig), "MfccConfig": (B200Mfcc, B200MfccConfig),
+             "SpectrogramConfig": (B200Spectrogram, B200SpectrogramConfig),
+             "LogSpectrogramConfig": (B200LogSpectrogram, B200LogSpectrogramConfig)}
+    if kind not in table:
+        raise ValueError(f"unsupported reference config type {kind}")
+    cls, ccls = table[kind]
+    d = {k: v for k, v in cfg.to_dict().items() if k in ccls.__dataclass_fields__}
+    d["device"] = device
+    return cls(ccls(**d))

@@ -1,0 +1,277 @@
+"""
+Config normalisation: any of the reference's Kaldi-family config dataclasses -> one
+``FeaturePlan`` (integer sizes + flags + float32 constant tables) that the C ABI consumes.
+
+The tables are built with the *same float32 torch op sequence* as the reference so they are
+bit-identical to its ``_window`` / ``_fb`` / ``_dct`` / ``_lifter`` parameters
+(lhotse/features/kaldi/layers.py:921-940, :960-1017, :873-907, :697-706, :681-695); tests assert
+that.  Only table construction happens here (once per extractor, a few hundred KB): the
+per-sample arithmetic lives exclusively in the CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+EPSILON = 1e-10  # lhotse/utils.py:50
+LOG_EPSILON = math.log(EPSILON)  # lhotse/utils.py:51 — the collation pad value
+
+FEATURE_KINDS = {"fbank": 0, "mfcc": 1, "spectrogram": 2, "log-spectrogram": 3}
+ENERGY_LHOTSE, ENERGY_KALDI = 0, 1
+WINDOWS = ("hamming", "hanning", "povey", "rectangular", "blackman")
+
+
+def next_power_of_2(x: int) -> int:
+    return 1 if x == 0 else 2 ** (x - 1).bit_length()  # layers.py:951
+
+
+def make_window(L: int, window_type: str, blackman_coeff: float = 0.42, torchaudio_blackman: bool = False) -> np.ndarray:
+    if window_type == "hanning":
+        w = torch.hann_window(L, periodic=False)
+    elif window_type == "hamming":
+        w = torch.hamming_window(L, periodic=False, alpha=0.54, beta=0.46)
+    elif window_type == "povey":
+        w = torch.hann_window(L, periodic=False).pow(0.85)
+    elif window_type == "rectangular":
+        w = torch.ones(L, dtype=torch.float32)
+    elif window_type == "blackman":
+        # lhotse: 2*pi/L (layers.py:931); torchaudio/kaldi: 2*pi/(L-1) (kaldi.py:104)
+        a = 2 * math.pi / (L - 1 if torchaudio_blackman else L)
+        k = torch.arange(L, dtype=torch.float32)
+        w = blackman_coeff - 0.5 * torch.cos(a * k) + (0.5 - blackman_coeff) * torch.cos(2 * a * k)
+    else:
+        raise ValueError(f"Invalid window type: {window_type}")
+    return w.to(torch.float32).numpy().copy()
+
+
+def _lin2mel(x):
+    # np.log on a torch tensor evaluates in numpy and wraps back to a tensor — the reference does
+    # exactly this (layers.py:943), and torch.log would differ in the last ulp of a few entries.
+    return 1127.0 * np.log(1 + x / 700)
+
+
+def make_mel_bank(
+    num_filters: int,
+    fft_length: int,
+    sampling_rate: int,
+    low_freq: float,
+    high_freq: float,
+    torchaudio_compatible: bool = True,
+    norm_filters: bool = False,
+) -> np.ndarray:
+    """Dense (K = N//2 + 1, M) float32 bank, equal to the reference's ``_fb``."""
+    M, N, sr = num_filters, fft_length, sampling_rate
+    if torchaudio_compatible:
+        if M <= 3:
+            raise ValueError("Must have at least 3 mel bins")  # layers.py:976
+        if N % 2 != 0:
+            raise ValueError("torchaudio-compatible mel scale needs an even fft length")  # :977
+        nyquist = 0.5 * sr
+        hi = high_freq + nyquist if high_freq <= 0.0 else high_freq
+        if not (0.0 <= low_freq < nyquist and 0.0 < hi <= nyquist and low_freq < hi):
+            raise ValueError(f"Bad values in options: low-freq {low_freq} and high-freq {hi} vs. nyquist {nyquist}")
+        mel_lo = _lin2mel(low_freq)
+        mel_hi = _lin2mel(hi)
+        delta = (mel_hi - mel_lo) / (M + 1)
+        b = torch.arange(M).unsqueeze(1)
+        left = mel_lo + b * delta
+        center = mel_lo + (b + 1.0) * delta
+        right = mel_lo + (b + 2.0) * delta
+        mel = _lin2mel((sr / N) * torch.arange(N / 2)).unsqueeze(0)
+        up = (mel - left) / (center - left)
+        down = (right - mel) / (right - center)
+        bank = torch.max(torch.zeros(1), torch.min(up, down))  # (M, N/2)
+        bank = torch.nn.functional.pad(bank, (0, 1), mode="constant", value=0).T
+        return np.ascontiguousarray(bank.to(torch.float32).numpy())
+    # legacy numpy scale (layers.py:873-907)
+    hi = high_freq
+    if hi is None or hi == 0:
+        hi = sr / 2
+    if hi < 0:
+        hi = sr / 2 + hi
+    melfc = np.linspace(1127.0 * np.log(1 + low_freq / 700), 1127.0 * np.log(1 + hi / 700), M + 2)
+    mels = 1127.0 * np.log(1 + np.linspace(0, sr, N) / 700)
+    K = int(N / 2 + 1)
+    B = np.zeros((K, M), dtype=np.float32)
+    j = np.arange(int(N / 2))
+    for k in range(M):
+        l, c, r = melfc[k], melfc[k + 1], melfc[k + 2]
+        mj = mels[: int(N / 2)]
+        inside = (l < mj) & (mj < r)
+        rising = inside & (mj <= c)
+        falling = inside & (mj > c)
+        B[j[rising], k] = (mj[rising] - l) / (c - l)
+        B[j[falling], k] = (r - mj[falling]) / (r - c)
+    if norm_filters:
+        B = B / np.sum(B, axis=0, keepdims=True)
+    return np.ascontiguousarray(B.astype(np.float32))
+
+
+def make_dct(num_ceps: int, num_filters: int) -> np.ndarray:
+    n = torch.arange(float(num_filters)).unsqueeze(1)
+    k = torch.arange(float(num_ceps))
+    dct = torch.cos(math.pi / float(num_filters) * (n + 0.5) * k)
+    dct[:, 0] *= 1.0 / math.sqrt(2.0)
+    dct *= math.sqrt(2.0 / float(num_filters))
+    return np.ascontiguousarray(dct.to(torch.float32).numpy())
+
+
+def make_lifter(num_ceps: int, Q: float) -> Optional[np.ndarray]:
+    if Q == 0:
+        return None
+    v = 1 + 0.5 * Q * torch.sin(math.pi * torch.arange(num_ceps, dtype=torch.float32) / Q)
+    return np.ascontiguousarray(v.to(torch.float32).numpy())
+
+
+@dataclass
+class FeaturePlan:
+    feature: str
+    sampling_rate: int
+    L: int
+    S: int
+    N: int
+    num_filters: int = 0
+    num_ceps: int = 0
+    snip_edges: bool = False
+    remove_dc_offset: bool = True
+    use_energy: bool = False
+    raw_energy: bool = True
+    use_fft_mag: bool = False
+    energy_style: int = ENERGY_LHOTSE
+    preemph_coeff: float = 0.97
+    energy_floor: float = EPSILON
+    mel_floor: float = float(torch.finfo(torch.float).eps)  # layers.py:533-535
+    log_spec_eps: float = 1e-15  # layers.py:467
+    dither: float = 0.0
+    window: np.ndarray = field(default=None, repr=False)
+    mel_bank: Optional[np.ndarray] = field(default=None, repr=False)
+    dct: Optional[np.ndarray] = field(default=None, repr=False)
+    lifter: Optional[np.ndarray] = field(default=None, repr=False)
+
+    @property
+    def K(self) -> int:
+        return self.N // 2 + 1
+
+    @property
+    def feature_dim(self) -> int:
+        if self.feature == "fbank":
+            return self.num_filters + (1 if self.use_energy else 0)
+        if self.feature == "mfcc":
+            return self.num_ceps
+        return self.K
+
+    def num_frames(self, n: int) -> int:
+        """layers.py:747-753 (the in-layer twin of utils.py:424-434)."""
+        if self.snip_edges:
+            return 0 if n < self.L else 1 + (n - self.L) // self.S
+        return (n + self.S // 2) // self.S
+
+    def tables_blob(self) -> np.ndarray:
+        """All constant tables in one float32 vector (what rank 0 broadcasts over NCCL)."""
+        parts = [self.window]
+        for t in (self.mel_bank, self.dct, self.lifter):
+            if t is not None:
+                parts.append(t.reshape(-1))
+        return np.concatenate(parts).astype(np.float32)
+
+    def load_tables_blob(self, blob: np.ndarray) -> None:
+        o = 0
+        self.window = blob[o : o + self.L].copy(); o += self.L
+        if self.mel_bank is not None:
+            n = self.mel_bank.size
+            self.mel_bank = blob[o : o + n].reshape(self.mel_bank.shape).copy(); o += n
+        if self.dct is not None:
+            n = self.dct.size
+            self.dct = blob[o : o + n].reshape(self.dct.shape).copy(); o += n
+        if self.lifter is not None:
+            n = self.lifter.size
+            self.lifter = blob[o : o + n].copy(); o += n
+        assert o == blob.size
+
+
+def _get(cfg: Any, *names, default=None):
+    for n in names:
+        if hasattr(cfg, n) and getattr(cfg, n) is not None:
+            return getattr(cfg, n)
+    return default
+
+
+def build_plan(feature: str, cfg: Any) -> FeaturePlan:
+    """Accepts our configs, lhotse's FbankConfig/MfccConfig/SpectrogramConfig/LogSpectrogramConfig
+    (extractors.py:24-63, :156-197, :266-293, :376-403), TorchaudioFbankConfig/TorchaudioMfccConfig/
+    TorchaudioSpectrogramConfig (fbank.py:11-39, mfcc.py:9-39, spectrogram.py:11-31) and
+    KaldifeatFbankConfig/KaldifeatMfccConfig (kaldifeat.py:149-175, :218-246), duck-typed by field names."""
+    if feature not in FEATURE_KINDS:
+        raise ValueError(f"unknown feature kind {feature}")
+    frame = _get(cfg, "frame_opts", default=cfg)  # kaldifeat nests the frame options
+    melo = _get(cfg, "mel_opts", default=cfg)
+    is_torchaudio = hasattr(cfg, "preemphasis_coefficient")
+    is_kaldifeat = hasattr(cfg, "frame_opts")
+    sr = int(_get(frame, "sampling_rate", default=16000))
+    frame_length = float(_get(frame, "frame_length", default=0.025))
+    frame_shift = float(_get(frame, "frame_shift", default=0.01))
+    L = int(math.floor(frame_length * sr))  # layers.py:114
+    S = int(math.floor(frame_shift * sr))  # layers.py:116
+    if L < 2 or S < 1:
+        raise ValueError(f"degenerate frame geometry L={L} S={S}")
+    rpo2 = bool(_get(frame, "round_to_power_of_two", default=True))
+    N = next_power_of_2(L) if rpo2 else L
+    window_type = _get(frame, "window_type", default="povey")
+    dither = float(_get(frame, "dither", default=0.0))
+    if dither != 0.0:
+        raise ValueError(
+            "dither != 0 is not supported: the reference draws it from the global torch RNG "
+            "(layers.py:190-193), which cannot be reproduced on device; add dither to the waveform upstream."
+        )
+    vtln = float(_get(melo, "vtln_warp", default=1.0))
+    if vtln != 1.0:
+        raise ValueError("vtln_warp != 1.0 is not supported")
+    if bool(_get(cfg, "htk_compat", default=False)):
+        raise ValueError("htk_compat=True is not supported")
+    if not bool(_get(cfg, "use_log_fbank", default=True)):
+        raise ValueError("use_log_fbank=False is not supported")
+    use_fft_mag = bool(_get(cfg, "use_fft_mag", default=False))
+    if hasattr(cfg, "use_power") and not cfg.use_power:
+        use_fft_mag = True
+    plan = FeaturePlan(
+        feature=feature,
+        sampling_rate=sr,
+        L=L,
+        S=S,
+        N=N,
+        snip_edges=bool(_get(frame, "snip_edges", default=False)),
+        remove_dc_offset=bool(_get(frame, "remove_dc_offset", default=True)),
+        use_energy=bool(_get(cfg, "use_energy", default=False)),
+        raw_energy=bool(_get(cfg, "raw_energy", default=True)),
+        use_fft_mag=use_fft_mag,
+        energy_style=ENERGY_KALDI if (is_torchaudio or is_kaldifeat) else ENERGY_LHOTSE,
+        preemph_coeff=float(_get(frame, "preemph_coeff", "preemphasis_coefficient", default=0.97)),
+        energy_floor=float(_get(cfg, "energy_floor", default=EPSILON)),
+        dither=dither,
+    )
+    plan.window = make_window(
+        L, window_type, blackman_coeff=float(_get(frame, "blackman_coeff", default=0.42)),
+        torchaudio_blackman=is_torchaudio or is_kaldifeat,
+    )
+    if feature in ("fbank", "mfcc"):
+        M = int(_get(melo, "num_filters", "num_mel_bins", "num_bins", default=80 if feature == "fbank" else 23))
+        plan.num_filters = M
+        plan.mel_bank = make_mel_bank(
+            M, N, sr,
+            float(_get(melo, "low_freq", default=20.0)),
+            float(_get(melo, "high_freq", default=-400.0)),
+            torchaudio_compatible=bool(_get(cfg, "torchaudio_compatible_mel_scale", default=True)),
+            norm_filters=bool(_get(cfg, "norm_filters", default=False)),
+        )
+    if feature == "mfcc":
+        C = int(_get(cfg, "num_ceps", default=13))
+        if C > plan.num_filters:
+            raise ValueError("num_ceps cannot exceed the number of mel filters")
+        plan.num_ceps = C
+        plan.dct = make_dct(C, plan.num_filters)
+        plan.lifter = make_lifter(C, float(_get(cfg, "cepstral_lifter", default=22)))
+    return plan

@@ -1,0 +1,172 @@
+"""Parity tests proper: CUDA kernels, called through the C ABI (lhotse_b200.engine.Engine ->
+libb200feat.so), against (a) the committed golden vectors of the real reference, (b) the oracle
+on seeded inputs, (c) size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import gate, load_golden, oracle_cfg
+from lhotse_b200 import (B200Fbank, B200FbankConfig, B200LogSpectrogram, B200LogSpectrogramConfig, B200Mfcc,
+                         B200MfccConfig, B200Spectrogram, B200SpectrogramConfig, LOG_EPSILON)
+from lhotse_b200.engine import B200FeatError
+from oracle import kaldi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TYPES = {"fbank": (B200Fbank, B200FbankConfig), "mfcc": (B200Mfcc, B200MfccConfig),
+         "spectrogram": (B200Spectrogram, B200SpectrogramConfig),
+         "log-spectrogram": (B200LogSpectrogram, B200LogSpectrogramConfig)}
+GOLD = load_golden()
+IDS = [f"{i}-{c['feature']}-{c['kind']}-{c['n']}" for i, c, _, _ in GOLD]
+
+
+def make(feature, cfg, kernel="auto"):
+    cls, ccls = TYPES[feature]
+    ext = cls(ccls(kernel=kernel, **cfg))
+    try:
+        ext.engine
+    except B200FeatError as e:
+        if e.code == -2 and kernel == "fast":
+            pytest.skip("plan not supported by the fast kernel")
+        raise
+    return ext
+
+
+def kernels_for(ext):
+    """Every kernel that supports the plan is tested (generic always; fast when AUTO picks it)."""
+    return ["generic"] if ext.engine.kernel == "generic" else ["generic", "fast"]
+
+
+@pytest.mark.parametrize("i,c,x,y", GOLD, ids=IDS)
+def test_golden_vectors(i, c, x, y):
+    sr = c["cfg"].get("sampling_rate", 16000)
+    truth = O.extract(x, oracle_cfg(c["feature"], c["cfg"]), dtype=torch.float64)
+    for k in kernels_for(make(c["feature"], c["cfg"])):
+        ext = make(c["feature"], c["cfg"], kernel=k)
+        got = ext.extract(x, sr)
+        assert got.dtype == np.float32 and got.shape == y.shape, (k, got.shape)  # frame counts: bit-exact
+        ok, msg = gate(got, y, truth, c["feature"], c["cfg"].get("use_energy", False))
+        assert ok, f"kernel={k}: {msg}"
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fast"])
+def test_ragged_batch_equals_per_cut(kernel):
+    rs = np.random.RandomState(5)
+    lens = [159, 160, 1599, 16000, 16001, 23456, 480, 100000, 16080]
+    xs = [(0.1 * rs.randn(n)).astype(np.float32) for n in lens]
+    ext = make("fbank", {}, kernel=kernel)
+    batch = ext.extract_batch(xs, 16000)
+    assert isinstance(batch, list) and len(batch) == len(xs)
+    cfg = O.OracleConfig()
+    for x, got in zip(xs, batch):
+        ref = O.extract(x, cfg)
+        truth = O.extract(x, cfg, dtype=torch.float64)
+        assert got.shape == ref.shape
+        ok, msg = gate(got, ref, truth, "fbank")
+        assert ok, msg
+        assert np.array_equal(got, ext.extract(x, 16000))  # batch item == single extract, bit for bit
+    # torch inputs (device-resident path) give the same bits as the host path
+    tb = ext.extract_batch([torch.from_numpy(x) for x in xs], 16000)
+    for a, b in zip(batch, tb):
+        assert b.is_cuda and np.array_equal(a, b.cpu().numpy())
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fast"])
+def test_padded_mode_and_int16(kernel):
+    rs = np.random.RandomState(6)
+    pcm = [np.clip(rs.randn(n) * 3000, -32768, 32767).astype(np.int16) for n in (4000, 16000, 9999)]
+    ext = make("fbank", {}, kernel=kernel)
+    feats, lens = ext.extract_batch_padded([torch.from_numpy(p.astype(np.float32) / 32768.0) for p in pcm], 16000)
+    assert feats.shape == (3, 100, 80) and lens.tolist() == [25, 100, 62]
+    f = feats.cpu().numpy()
+    assert np.all(f[0, 25:] == np.float32(LOG_EPSILON)) and np.all(f[2, 62:] == np.float32(LOG_EPSILON))
+    cfg = O.OracleConfig()
+    for i, p in enumerate(pcm):
+        x = p.astype(np.float32) / 32768.0
+        ok, msg = gate(f[i, : lens[i]], O.extract(x, cfg), O.extract(x, cfg, dtype=torch.float64), "fbank")
+        assert ok, msg
+    # int16 staging: same bits as float32 staging of x/32768
+    i16 = ext.extract_batch(pcm, 16000)
+    f32 = ext.extract_batch([p.astype(np.float32) / 32768.0 for p in pcm], 16000)
+    for a, b in zip(i16, f32):
+        assert np.array_equal(a, b)
+
+
+def test_headline_size_properties():
+    """BASELINE config 2 at full size (64 x 10 s): shapes, determinism, shift- and batch-invariance."""
+    torch.manual_seed(0)
+    B, n = 64, 160000
+    x = (0.1 * torch.randn(B, n)).cuda()
+    ext = make("fbank", {})
+    y = ext.extract_batch(x, 16000)
+    assert y.shape == (B, 1000, 80) and y.is_cuda and torch.isfinite(y).all()
+    y2 = ext.extract_batch(x, 16000)
+    assert torch.equal(y, y2)  # deterministic
+    perm = torch.randperm(B)
+    yp = ext.extract_batch(x[perm.cuda()], 16000)
+    assert torch.equal(yp, y[perm.cuda()])  # cuts are independent
+    # frames away from the edges depend only on their own 400 samples: shifting the cut by one hop
+    # shifts the features by one frame, bit for bit
+    ys = ext.extract_batch(x[:4, 160:], 16000)
+    assert torch.equal(ys[:, 2:900], y[:4, 3:901])
+    # a sample of cuts against the oracle
+    cfg = O.OracleConfig()
+    for b in (0, 31, 63):
+        xb = x[b].cpu().numpy()
+        ok, msg = gate(y[b].cpu().numpy(), O.extract(xb, cfg), O.extract(xb, cfg, dtype=torch.float64), "fbank")
+        assert ok, msg
+    # generic and fast kernels agree to fp32 noise
+    if ext.engine.kernel == "fast":
+        yg = make("fbank", {}, kernel="generic").extract_batch(x[:8], 16000)
+        assert torch.allclose(yg, y[:8], rtol=1e-4, atol=2e-4)
+
+
+def test_mfcc_config3_tolerance():
+    """BASELINE config 3: Mfcc(num_ceps=13, num_mel_bins=23), gate like test_kaldi_features.py:116-122."""
+    torch.manual_seed(1)
+    x = (0.1 * torch.randn(8, 160000)).numpy()
+    ext = make("mfcc", dict(num_ceps=13, num_mel_bins=23))
+    y = ext.extract_batch(x, 16000)
+    assert y.shape == (8, 1000, 13)
+    cfg = O.OracleConfig(feature="mfcc", num_ceps=13, num_filters=23)
+    for b in range(8):
+        np.testing.assert_allclose(y[b], O.extract(x[b], cfg), rtol=1e-3, atol=2e-3)
+
+
+def test_device_tables_roundtrip():
+    ext = make("mfcc", {})
+    e = ext.engine
+    assert np.array_equal(e.get_table(0), ext.plan.window)
+    assert np.array_equal(e.get_table(1).reshape(ext.plan.mel_bank.shape), ext.plan.mel_bank)
+    assert np.array_equal(e.get_table(2).reshape(ext.plan.dct.shape), ext.plan.dct)
+    assert np.array_equal(e.get_table(3), ext.plan.lifter)
+    tw = e.get_table(4).reshape(-1, 2)
+    k = np.arange(tw.shape[0])
+    assert np.allclose(tw[:, 0], np.cos(2 * np.pi * k / tw.shape[0]), atol=1e-7)
+    st = e.stats()
+    assert st["calls"] == 0
+
+
+def test_errors_do_not_abort():
+    ext = make("fbank", {})
+    with pytest.raises(ValueError):
+        ext.extract(np.zeros(100, dtype=np.float32), 16000)
+    with pytest.raises(ValueError):
+        ext.extract_batch([np.zeros(16000, dtype=np.float32), np.zeros(50, dtype=np.float32)], 16000)
+    assert ext.extract(np.zeros(1600, dtype=np.float32), 16000).shape == (10, 80)  # still usable
+
+
+def test_concurrent_streams():
+    ext = make("fbank", {})
+    torch.manual_seed(2)
+    xs = [(0.1 * torch.randn(16, 32000)).cuda() for _ in range(4)]
+    want = [ext.extract_batch(x, 16000) for x in xs]
+    streams = [torch.cuda.Stream() for _ in xs]
+    got = []
+    for s, x in zip(streams, xs):
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            got.append(ext.extract_batch(x, 16000))
+    torch.cuda.synchronize()
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
