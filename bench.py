@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""
+bench.py — hours-of-audio/sec, Fbank-80 @ 16 kHz (25 ms / 10 ms, N = 512), batches of 10 s cuts.
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 path (this repository)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port)
+
+One "step" = one pass of the hot path over one batch of synthetic cuts (`--batch` cuts of
+`--cut-seconds`): a single fused kernel launch on a device-resident ragged batch.
+  value  : whole-job hours-of-audio/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e    : the same metric through the C-ABI host call (pinned host samples in, pinned host
+           features out; H2D + kernel + D2H inside the timed region)
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md "Measurement"
+Multi-GPU: one process per GPU under torchrun, cuts sharded per rank, weak scaling, no data-path
+collective (table broadcast at start + a MAX-reduce of the elapsed time only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 16000
+METRIC = "hours-of-audio/sec Fbank-80@16kHz, 10s cuts"
+UNIT = "h_audio/s"
+BYTES_PER_FRAME = 160 * 4 + 80 * 4  # 640 B read + 320 B written per frame
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle/kaldi_oracle.py, torch-CPU ops == the reference's own
+# op chain) on the host cores, one single-threaded worker process per core, per-cut extract —
+# the reference's fastest CPU mode.
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, ncuts, nsamp = args
+    import numpy as np
+    import torch
+
+    from oracle import kaldi_oracle as O
+
+    torch.set_num_threads(1)
+    rs = np.random.RandomState(seed)
+    cfg = O.OracleConfig()
+    xs = [(0.1 * rs.randn(nsamp)).astype(np.float32) for _ in range(min(ncuts, 4))]
+    O.extract(xs[0], cfg)  # warm
+    t0 = time.perf_counter()
+    for i in range(ncuts):
+        O.extract(xs[i % len(xs)], cfg)
+    return time.perf_counter() - t0
+
+
+def cpu_pass(pool, procs, cuts_per_worker, nsamp):
+    t0 = time.perf_counter()
+    times = pool.map(_cpu_worker, [(1000 + i, cuts_per_worker, nsamp) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    slowest = max(times)
+    hours = procs * cuts_per_worker * nsamp / SR / 3600.0
+    return hours / slowest, slowest, wall
+
+
+def cpu_pool(procs):
+    import multiprocessing as mp
+
+    return mp.get_context("fork").Pool(procs)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax = float(r[2]); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return  # the CPU arm runs once per box
+    procs = host_cores()
+    nsamp = int(args.cut_seconds * SR)
+    per = args.cpu_cuts_per_worker
+    pool = cpu_pool(procs)
+    try:
+        for _ in range(args.warmup):
+            cpu_pass(pool, procs, max(1, per // 8), nsamp)
+        vals, slow = [], []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            v, s, _ = cpu_pass(pool, procs, per, nsamp)
+            vals.append(v); slow.append(s)
+        total = time.perf_counter() - t0
+    finally:
+        pool.close()
+    hours = args.steps * procs * per * nsamp / SR / 3600.0
+    value = hours / sum(slow)
+    sample = f"{procs} procs x {per} cuts x {args.cut_seconds:g}s per step, torch 1 thread/proc, per-cut extract"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(slow) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Fbank-80 16kHz 25ms/10ms N=512, {args.cut_seconds:g}s cuts (BASELINE configs[1]) — bounded CPU sample",
+                   "cuts_per_step": procs * per, "parallelism": f"{procs} cpu procs"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    nsamp = int(args.cut_seconds * SR)
+
+    # CPU baseline first (forks workers: must precede CUDA initialisation), rank 0 at N=1 only
+    cpu_baseline = None
+    if world == 1 and not args.skip_cpu_baseline:
+        procs = host_cores()
+        per = args.cpu_cuts_per_worker
+        pool = cpu_pool(procs)
+        try:
+            cpu_pass(pool, procs, max(1, per // 8), nsamp)
+            v, slowest, _ = cpu_pass(pool, procs, per, nsamp)
+        finally:
+            pool.close()
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                        "sample": f"{procs} procs x {per} cuts x {args.cut_seconds:g}s, {slowest:.2f}s slowest worker "
+                                  "(oracle/kaldi_oracle.py: the reference's torch-CPU op chain, 1 thread/proc, per-cut extract)"}
+
+    import numpy as np
+    import torch
+
+    import lhotse_b200 as lb
+    from lhotse_b200 import dist as lbd
+    from lhotse_b200.engine import Engine
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    rank, world, local = lbd.init_distributed()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    cfg = lb.B200FbankConfig(device=f"cuda:{local}", kernel=args.kernel)
+    plan = lb.build_plan("fbank", cfg)
+    lbd.broadcast_plan_tables(plan)  # NCCL broadcast of the constant tables (rank 0's bits everywhere)
+    eng = Engine(plan, device=dev, kernel=args.kernel)
+
+    B = args.batch
+    torch.manual_seed(1234 + rank)
+    x = torch.empty(B * nsamp, dtype=torch.float32, device=dev)
+    chunk = 256
+    for i in range(0, B, chunk):  # synthetic 0.1*N(0,1) audio, generated on device
+        j = min(B, i + chunk)
+        x[i * nsamp: j * nsamp] = 0.1 * torch.randn((j - i) * nsamp, device=dev)
+    lens = [nsamp] * B
+    offs = [i * nsamp for i in range(B)]
+    meta, tot = eng.plan_batch(lens, offs)
+    meta_dev = torch.from_numpy(meta).to(dev)
+    out = torch.empty((tot.total_rows, eng.feature_dim), dtype=torch.float32, device=dev)
+    frames = int(tot.total_rows)
+    hours_per_step = B * nsamp / SR / 3600.0
+
+    def step():
+        eng.extract_device(x, lens, offs, out=out, meta_dev=meta_dev, totals=tot)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.stats()["kernel_launches"]
+    lbd.barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    lbd.barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    launches = eng.stats()["kernel_launches"] - launches0
+    elapsed_max_ms = lbd.all_reduce_stats([elapsed_ms], "max")[0]
+    value = world * hours_per_step * args.steps / (elapsed_max_ms / 1000.0)
+
+    # ---- e2e: C-ABI host call, pinned host buffers, H2D + kernel + D2H inside the timed region
+    Be = min(B, args.e2e_batch)
+    hx = torch.empty(Be * nsamp, dtype=torch.float32, pin_memory=True)
+    hx.copy_(x[: Be * nsamp])
+    hout = torch.empty((Be * (frames // B), eng.feature_dim), dtype=torch.float32, pin_memory=True)
+    elens = [nsamp] * Be
+    for _ in range(3):
+        eng.extract_host(hx, elens, out=hout)
+    lbd.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        eng.extract_host(hx, elens, out=hout)
+    e2e_s = time.perf_counter() - t0
+    lbd.barrier()
+    e2e_max = lbd.all_reduce_stats([e2e_s], "max")[0]
+    e2e_value = world * (Be * nsamp / SR / 3600.0) * args.e2e_steps / e2e_max
+    clocks = sampler.stop() if rank == 0 else None
+
+    # correctness spot check of what was timed (cheap, outside the timed region)
+    assert torch.isfinite(out[:: max(1, frames // 4096)]).all()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kern_ms = statistics.mean(per_launch_ms)
+        achieved = frames * BYTES_PER_FRAME / (kern_ms / 1000.0) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("kernel") == eng.kernel and tj.get("frames"):
+                    traffic = tj["dram_bytes"] * frames / tj["frames"]
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"Fbank-80 16kHz 25ms/10ms N=512 (L=400,S=160), {B} x {args.cut_seconds:g}s cuts per GPU per step (BASELINE configs[1])",
+                       "cuts_per_gpu_per_step": B, "frames_per_gpu_per_step": frames, "kernel": eng.kernel,
+                       "parallelism": f"dp{world} (cuts sharded per rank, no data-path collective)",
+                       "l2_policy": f"inputs {B * nsamp * 4 / 2**20:.0f} MiB + outputs {frames * 320 / 2**20:.0f} MiB per step > 126 MiB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Be * nsamp * 4,
+                    "d2h_bytes_per_step": int(hout.numel()) * 4, "cuts_per_step": Be, "steps": args.e2e_steps,
+                    "api": "b200feat_extract_host (C ABI) via Engine.extract_host, pinned host in/out"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": frames * BYTES_PER_FRAME,
+                         "read_only_frac": frames * 640 / (kern_ms / 1000.0) / 1e9 / peak},
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=2048, help="cuts per GPU per step")
+    ap.add_argument("--cut-seconds", type=float, default=10.0)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fast", "generic"])
+    ap.add_argument("--e2e-batch", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-cuts-per-worker", type=int, default=200)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,7 @@ struct b200feat_handle {
   b200feat_stats stats{};
   std::mutex stats_mu;
   HostRing ring;
+  Fast512Host fast;
 };
 
 namespace {
@@ -244,7 +245,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   }
   h->frames_per_tile = 1;
   if (h->kernel == B200FEAT_KERNEL_FAST) {
-    rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile);
+    rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
     if (rc) { cudaSetDevice(prev); b200feat_destroy(h); return fail(nullptr, rc, "fast512_prepare failed"); }
   }
 #undef UP
@@ -339,7 +340,7 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   db.pad_value = pad_value;
   if (db.num_tiles <= 0) return 0;
   if (h->kernel == B200FEAT_KERNEL_FAST) {
-    int rc = fast512_launch(h->plan, db, dt, h->sm_count, stream);
+    int rc = fast512_launch(h->plan, h->fast, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512 launch: ") + cudaGetErrorString((cudaError_t)rc));
   } else {
     const int w = h->generic_warps;

@@ -1,0 +1,92 @@
+"""
+Multi-GPU plumbing: one process per GPU, cuts sharded across ranks, no data-path collective.
+
+The path is embarrassingly parallel (cuts are independent), so the only communication is
+  * a broadcast of the constant-table blob from rank 0 at start-up (every rank then runs on
+    bit-identical window / mel / DCT tables), and
+  * reductions of counters / elapsed time for reporting.
+Sharding is the reference's own job split: rank r of W takes cuts r, r+W, ...
+(`LazySlicer(k=r, n=W)`, lhotse/cut/set.py:2158-2160; sampler-level equivalent
+lhotse/dataset/sampling/base.py:143-164).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple, TypeVar
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .plan import FeaturePlan
+
+T = TypeVar("T")
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0)))
+
+
+def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialises torch.distributed from the torchrun environment (no-op for world size 1)."""
+    rank, world, local = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, world, local
+
+
+def shard_slice(items: Sequence[T], rank: int, world: int) -> List[T]:
+    """rank::world striding — identical to LazySlicer(k=rank, n=world)."""
+    return list(items[rank::world])
+
+
+def shard_iter(items: Iterable[T], rank: int, world: int) -> Iterator[T]:
+    for i, it in enumerate(items):
+        if i % world == rank:
+            yield it
+
+
+def unshard(per_rank: Sequence[Sequence[T]]) -> List[T]:
+    """Inverse of shard_slice over all ranks (the order `combine` restores)."""
+    world = len(per_rank)
+    total = sum(len(p) for p in per_rank)
+    out: List[Optional[T]] = [None] * total
+    for r, part in enumerate(per_rank):
+        out[r::world] = list(part)
+    return out  # type: ignore
+
+
+def _comm_device() -> torch.device:
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def broadcast_plan_tables(plan: FeaturePlan, src: int = 0) -> FeaturePlan:
+    """Every rank ends up with rank `src`'s float32 tables, bit for bit (~90 KB over NCCL/NVLink)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return plan
+    blob = torch.from_numpy(plan.tables_blob()).to(_comm_device())
+    dist.broadcast(blob, src=src)
+    plan.load_tables_blob(blob.cpu().numpy())
+    return plan
+
+
+def all_reduce_stats(values: Sequence[float], op: str = "sum") -> List[float]:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(values)
+    t = torch.tensor(list(values), dtype=torch.float64, device=_comm_device())
+    dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN}[op])
+    return t.cpu().tolist()
+
+
+def barrier():
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

@@ -29,7 +29,8 @@ Reference citations (relative to /root/reference):
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
+from dataclasses import astuple, dataclass
+from functools import lru_cache
 from typing import Optional, Tuple
 
 import numpy as np
@@ -212,13 +213,32 @@ def _log_energy(frames: torch.Tensor, floor: float) -> torch.Tensor:
     return e
 
 
+def _frames_view(x: torch.Tensor, L: int, S: int, snip_edges: bool) -> torch.Tensor:
+    """Overlapping-frame view of the (reflect-padded) waveform — the cheap formulation the reference
+    uses (layers.py:753-772: flip/cat then a strided view); `frame_index_matrix` is its closed form
+    and tests assert the two agree."""
+    n = x.numel()
+    T = num_frames_layer(n, L, S, snip_edges)
+    if T <= 0:
+        raise ValueError(f"input of {n} samples yields no frames")
+    if not snip_edges:
+        left = (L - S) // 2
+        right = (T - 1) * S + L - n - left
+        if left > n or right > n:
+            raise ValueError(f"input of {n} samples is too short for reflect padding ({left},{right})")
+        parts = [x[:left].flip(0), x]
+        if right > 0:
+            parts.append(x[n - right:].flip(0))
+        x = torch.cat(parts)
+    return x.unfold(0, L, S)[:T]
+
+
 def windowed_frames(x: torch.Tensor, cfg: OracleConfig):
     """(n,) waveform -> ((T, N) zero-padded windowed frames, optional (T,) log-energy).
     layers.py:151-186 applied to the gather of layers.py:727-772."""
     assert cfg.dither == 0.0, "oracle is deterministic: dither must be 0"
     L, S, N = layer_sizes(cfg)
-    idx = torch.from_numpy(frame_index_matrix(x.numel(), L, S, cfg.snip_edges))
-    f = x[idx]  # (T, L)
+    f = _frames_view(x, L, S, cfg.snip_edges)  # (T, L) strided view, == x[frame_index_matrix(...)]
     if cfg.remove_dc_offset:
         f = f - torch.mean(f, dim=1, keepdim=True)
     log_e = None
@@ -227,12 +247,30 @@ def windowed_frames(x: torch.Tensor, cfg: OracleConfig):
     if cfg.preemph_coeff != 0.0:
         prev = torch.cat((f[:, :1], f[:, :-1]), dim=1)  # replicate-left
         f = f - cfg.preemph_coeff * prev
-    f = f * make_window(L, cfg.window_type, dtype=x.dtype)
+    f = f * _cached_tables(astuple(cfg), x.dtype)[0]
     if N != L:
         f = torch.nn.functional.pad(f, (0, N - L))
     if cfg.use_energy and not cfg.raw_energy:
         log_e = _log_energy(f, cfg.energy_floor)
     return f, log_e
+
+
+@lru_cache(maxsize=64)
+def _cached_tables(cfg_key, dtype):
+    """The reference builds its tables once, in the module constructors (layers.py:117-119, :541-563,
+    :673-680); cache them per config so that timing this oracle is representative."""
+    cfg = OracleConfig(*cfg_key)
+    L, S, N = layer_sizes(cfg)
+    win = make_window(L, cfg.window_type, dtype=dtype)
+    fb = dct = lifter = None
+    if cfg.feature in ("fbank", "mfcc"):
+        fb = make_mel_bank(cfg, N)  # keeps the reference's transposed-view layout
+        fb = fb if fb.dtype == dtype else fb.to(dtype)
+    if cfg.feature == "mfcc":
+        dct = make_dct(cfg.num_ceps, cfg.num_filters).to(dtype)
+        lifter = make_lifter(cfg.num_ceps, cfg.cepstral_lifter)
+        lifter = None if lifter is None else lifter.to(dtype)
+    return win, fb, dct, lifter
 
 
 def extract(x, cfg: OracleConfig, dtype=torch.float32) -> np.ndarray:
@@ -252,7 +290,7 @@ def extract(x, cfg: OracleConfig, dtype=torch.float32) -> np.ndarray:
         if log_e is not None:
             out[:, 0] = log_e
     elif feat in ("fbank", "mfcc"):
-        fb = make_mel_bank(cfg, N).to(dtype)
+        _, fb, dct_t, lifter_t = _cached_tables(astuple(cfg), dtype)
         eps = torch.tensor(torch.finfo(torch.float).eps, dtype=dtype)
         # the reference multiplies a (1, T, K) batch (layers.py:571); keep the leading dim so the
         # same BLAS path (and rounding) is taken for tiny T
@@ -260,10 +298,9 @@ def extract(x, cfg: OracleConfig, dtype=torch.float32) -> np.ndarray:
         if feat == "fbank":
             out = mel if log_e is None else torch.cat((log_e.unsqueeze(-1), mel), dim=-1)
         else:
-            out = torch.matmul(mel.unsqueeze(0), make_dct(cfg.num_ceps, cfg.num_filters).to(dtype)).squeeze(0)
-            lifter = make_lifter(cfg.num_ceps, cfg.cepstral_lifter)
-            if lifter is not None:
-                out = out * lifter.to(dtype)
+            out = torch.matmul(mel.unsqueeze(0), dct_t).squeeze(0)
+            if lifter_t is not None:
+                out = out * lifter_t
             if log_e is not None:
                 # layers.py:722 writes `mfcc[:, 0] = log_e` on a 3-D tensor (broken upstream for
                 # batched input); the intended Kaldi semantics — C0 <- log-energy — is restated here.

@@ -27,12 +27,24 @@ def oracle_cfg(feature, cfg):
     return O.OracleConfig(feature=feature, **cfg)
 
 
-def linear_feature(feature):
-    return feature == "spectrogram"
+def _unit_tolerance(truth64, feature, use_energy, use_fft_mag):
+    """Element-wise tolerance 'unit' for one case (float64 arrays)."""
+    if feature in ("spectrogram", "log-spectrogram"):
+        # judge spectra in the linear domain: an fp32 FFT carries an amplitude error ~1e-6 of the
+        # frame's largest line, whatever the bin's own size (log() would blow that up arbitrarily)
+        lin = np.exp(truth64) if feature == "log-spectrogram" else truth64.copy()
+        body = lin[:, 1:] if use_energy else lin
+        peak = np.sqrt(np.abs(body).max(axis=1, keepdims=True)) if not use_fft_mag else np.abs(body).max(axis=1, keepdims=True)
+        delta = 2e-6 * peak
+        amp = np.sqrt(np.abs(lin)) if not use_fft_mag else np.abs(lin)
+        tol = RTOL * np.abs(lin) + (delta if use_fft_mag else 2 * amp * delta + delta ** 2) + 1e-30
+        return lin, tol
+    return truth64, ATOL + RTOL * np.abs(truth64)
 
 
-def gate(ours, ref32, truth64, feature, use_energy=False):
-    """Returns (ok, message)."""
+def gate(ours, ref32, truth64, feature, use_energy=False, use_fft_mag=False):
+    """Returns (ok, message).  max(err/tol) of ours must be <= max(1, NOISE_X * the same figure of
+    the fp32 reference itself)."""
     ours = np.asarray(ours, dtype=np.float64)
     ref32 = np.asarray(ref32, dtype=np.float64)
     truth64 = np.asarray(truth64, dtype=np.float64)
@@ -40,23 +52,21 @@ def gate(ours, ref32, truth64, feature, use_energy=False):
         return False, f"shape {ours.shape} != {ref32.shape}"
     if not np.all(np.isfinite(ours)):
         return False, "non-finite values"
-    err = np.abs(ours - truth64)
-    noise = np.abs(ref32 - truth64)
-    if linear_feature(feature):
-        lin = truth64[:, 1:] if use_energy else truth64
-        rowmax = np.abs(lin).max(axis=1, keepdims=True)
-        tol = 1e-5 * rowmax + RTOL * np.abs(truth64) + 1e-12
-        if use_energy:
-            tol[:, 0] = ATOL + RTOL * np.abs(truth64[:, 0])
-    else:
-        tol = ATOL + RTOL * np.abs(truth64)
-    if noise.max() > 0.05 * max(1.0, np.abs(truth64).max() * 1e-2):
-        return False, f"reference itself is {noise.max():.3e} away from the float64 truth: wrong config?"
-    tol = np.maximum(tol, NOISE_X * noise.max())
-    bad = err > tol
-    msg = (f"max|ours-truth|={err.max():.3e} max|ref32-truth|={noise.max():.3e} "
-           f"max|ours-ref32|={np.abs(ours - ref32).max():.3e} bad={int(bad.sum())}/{bad.size}")
-    return not bad.any(), msg
+    tdom, tol = _unit_tolerance(truth64, feature, use_energy, use_fft_mag)
+    to_dom = (lambda a: np.exp(a)) if feature == "log-spectrogram" else (lambda a: a)
+    o, r = to_dom(ours), to_dom(ref32)
+    if use_energy and feature in ("spectrogram", "log-spectrogram"):  # column 0 is a log-energy
+        o[:, 0], r[:, 0], tdom = ours[:, 0], ref32[:, 0], tdom.copy()
+        tdom[:, 0] = truth64[:, 0]
+        tol[:, 0] = ATOL + RTOL * np.abs(truth64[:, 0])
+    err = np.abs(o - tdom) / tol
+    noise = np.abs(r - tdom) / tol
+    if noise.max() > 50:
+        return False, f"reference itself is {noise.max():.1f} tolerance units from the float64 truth: wrong config?"
+    limit = max(1.0, NOISE_X * noise.max())
+    msg = (f"max err/tol ours={err.max():.3f} ref32={noise.max():.3f} limit={limit:.3f} "
+           f"max|ours-ref32|={np.abs(ours - ref32).max():.3e} bad={int((err > limit).sum())}/{err.size}")
+    return bool(err.max() <= limit), msg
 
 
 class OracleEngine:

@@ -45,7 +45,7 @@ def test_golden_vectors(i, c, x, y):
         ext = make(c["feature"], c["cfg"], kernel=k)
         got = ext.extract(x, sr)
         assert got.dtype == np.float32 and got.shape == y.shape, (k, got.shape)  # frame counts: bit-exact
-        ok, msg = gate(got, y, truth, c["feature"], c["cfg"].get("use_energy", False))
+        ok, msg = gate(got, y, truth, c["feature"], c["cfg"].get("use_energy", False), c["cfg"].get("use_fft_mag", False))
         assert ok, f"kernel={k}: {msg}"
 
 

@@ -20,7 +20,7 @@ def test_oracle_matches_golden(i, c, x, y):
     if np.array_equal(got, y):
         return  # bit-identical (same CPU / BLAS path as the generator)
     truth = O.extract(x, cfg, dtype=torch.float64)
-    ok, msg = gate(got, y, truth, c["feature"], c["cfg"].get("use_energy", False))
+    ok, msg = gate(got, y, truth, c["feature"], c["cfg"].get("use_energy", False), c["cfg"].get("use_fft_mag", False))
     assert ok, msg
     # different BLAS kernels (other CPU, other thread count) may move the last bits only
     np.testing.assert_allclose(got, y, rtol=1e-4, atol=1e-3 if c["feature"] == "mfcc" else 1e-4)
@@ -74,3 +74,13 @@ def test_oracle_bit_identical_to_live_reference():
             ref = cls(ccls(**c["cfg"])).extract(x, c["cfg"].get("sampling_rate", 16000))
             got = O.extract(x, oracle_cfg(c["feature"], c["cfg"]))
             assert np.array_equal(ref, got), f"case {i}: max diff {np.abs(ref - got).max()}"
+
+
+def test_strided_view_equals_closed_form_gather():
+    rs = np.random.RandomState(0)
+    for n, L, S, snip in ((159, 400, 160, False), (1000, 400, 160, False), (16080, 400, 160, False),
+                          (5000, 200, 80, False), (3000, 400, 160, True), (11025, 551, 220, False)):
+        x = torch.from_numpy(rs.randn(n).astype(np.float32))
+        a = O._frames_view(x, L, S, snip)
+        b = x[torch.from_numpy(O.frame_index_matrix(n, L, S, snip))]
+        assert torch.equal(a, b)
