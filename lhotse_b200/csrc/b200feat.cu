@@ -246,7 +246,13 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   h->frames_per_tile = 1;
   if (h->kernel == B200FEAT_KERNEL_FAST) {
     rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
-    if (rc) { cudaSetDevice(prev); b200feat_destroy(h); return fail(nullptr, rc, "fast512_prepare failed"); }
+    if (rc == B200FEAT_EUNSUPPORTED && desc->kernel == B200FEAT_KERNEL_AUTO) {
+      h->kernel = B200FEAT_KERNEL_GENERIC;  // e.g. the plan's tables do not fit the fast kernel's shared memory
+      h->frames_per_tile = 1;
+    } else if (rc) {
+      cudaSetDevice(prev); b200feat_destroy(h);
+      return fail(nullptr, rc, "fast kernel cannot be prepared for this plan (shared-memory footprint?)");
+    }
   }
 #undef UP
   cudaSetDevice(prev);

@@ -116,7 +116,6 @@ static inline size_t fast512_smem_bytes(const DevPlan &p, const Fast512Tables &t
   size_t b = (size_t)F512_HW * (F512_XBUF * 8 + F512_PBUF * 4);
   b += 16 * 16 * 8;                          // window pairs
   b += (size_t)p.M * 3 * 4 + (size_t)t.mel_nnz * 4;  // mel start/len/woff + weights
-  b += (size_t)F512_HW * F512_SLOTS * ((p.M + 3) & ~3) * 4 * (p.feature == B200FEAT_MFCC ? 1 : 0);  // log-mel staging
   return (b + 15) & ~(size_t)15;
 }
 
@@ -139,7 +138,6 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   int *s_mlen = s_mstart + p.M;
   int *s_mwoff = s_mlen + p.M;
   float *s_mw = reinterpret_cast<float *>(s_mwoff + p.M);
-  float *s_mlog = s_mw + ft.mel_nnz;  // MFCC only
   float2 *X = xall + (size_t)hw * F512_XBUF;
   float *P = pall + (size_t)hw * F512_PBUF;
 
@@ -315,7 +313,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
     } else {
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
       const int Mpad = (p.M + 3) & ~3;
-      float *mlog = s_mlog + (size_t)hw * F512_SLOTS * Mpad;
+      float *mlog = reinterpret_cast<float *>(X);  // the transpose tile is idle during the epilogue
       for (int j = 0; j < ft.mel_rounds; ++j) {
         const int m = l + 16 * j;
         const bool mv = m < p.M;
@@ -370,7 +368,8 @@ struct Fast512Host {
 };
 
 static inline bool fast512_supported(const DevPlan &p) {
-  return p.N == 512 && p.packed && p.L >= 2 && p.L <= 512 && p.M <= 512 && p.C <= 128;
+  return p.N == 512 && p.packed && p.L >= 2 && p.L <= 512 && p.C <= 128 &&
+         F512_SLOTS * ((p.M + 3) & ~3) <= 2 * F512_XBUF;  // log-mel staging reuses the transpose tile
 }
 
 template <typename T>
@@ -411,16 +410,12 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   if ((rc = f512_upload(win2, allocs, &hst.t.win2))) return rc;
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
-  int nnz = 1;
-  if (p.M) {
-    nnz = 0;
-    for (int m = 0; m < p.M; ++m) {
-      int first = -1, last = -1;
-      for (int k = 0; k < p.K; ++k)
-        if (bank[(size_t)k * p.M + m] != 0.f) { if (first < 0) first = k; last = k; }
-      if (first >= 0) nnz += last - first + 1;
-    }
-    if (nnz == 0) nnz = 1;
+  int nnz = 0;  // must match the packing of mel_w in b200feat_create (0 when there is no bank)
+  for (int m = 0; m < p.M; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < p.K; ++k)
+      if (bank[(size_t)k * p.M + m] != 0.f) { if (first < 0) first = k; last = k; }
+    if (first >= 0) nnz += last - first + 1;
   }
   hst.t.mel_nnz = nnz;
   hst.t.mel_rounds = (p.M + 15) / 16;

@@ -1,0 +1,71 @@
+"""World-size-2 `gloo` tests (CPU) of the multi-GPU host logic: rank::world sharding of cuts
+(the reference's LazySlicer split, set.py:2158-2160), bit-identical table broadcast, stat reductions."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lhotse_b200 import B200FbankConfig, build_plan
+from lhotse_b200 import dist as lbd
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    r, w, _ = lbd.init_distributed(backend="gloo")
+    assert (r, w) == (rank, world)
+    plan = build_plan("fbank", B200FbankConfig())
+    good = plan.tables_blob().copy()
+    if rank != 0:  # corrupt the non-root tables: the broadcast must restore rank 0's bits
+        plan.window[:] = 7.0
+        plan.mel_bank[:] = -1.0
+    lbd.broadcast_plan_tables(plan)
+    ok_tables = np.array_equal(plan.tables_blob(), good)
+    cuts = list(range(23))
+    mine = lbd.shard_slice(cuts, rank, world)
+    assert mine == list(lbd.shard_iter(cuts, rank, world))
+    frames = sum(100 + c for c in mine)
+    tot = lbd.all_reduce_stats([frames, len(mine)], "sum")
+    mx = lbd.all_reduce_stats([float(rank + 1)], "max")
+    lbd.barrier()
+    q.put((rank, ok_tables, mine, tot, mx))
+    dist.destroy_process_group()
+
+
+def test_world2_sharding_and_broadcast():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    shards = [r[2] for r in res]
+    assert all(r[1] for r in res), "tables differ after broadcast"
+    assert sorted(shards[0] + shards[1]) == list(range(23)) and not set(shards[0]) & set(shards[1])
+    assert lbd.unshard(shards) == list(range(23))
+    assert res[0][3] == res[1][3] == [float(sum(100 + c for c in range(23))), 23.0]
+    assert res[0][4] == res[1][4] == [2.0]
+
+
+def test_single_process_noops():
+    plan = build_plan("fbank", B200FbankConfig())
+    assert lbd.broadcast_plan_tables(plan) is plan
+    assert lbd.all_reduce_stats([1.0, 2.0]) == [1.0, 2.0]
+    assert lbd.shard_slice(list(range(10)), 1, 4) == [1, 5, 9]
