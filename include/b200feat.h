@@ -110,6 +110,7 @@ typedef struct b200feat_batch_totals {
   int64_t total_tiles;   /* work items of the selected kernel */
   int64_t span_samples;  /* elements the sample buffer must hold (last offset + last length) */
   int64_t out_floats;    /* floats the output buffer must hold for the chosen out_mode */
+  int64_t meta_words;    /* int64 words of meta actually written (what must reach the device) */
 } b200feat_batch_totals;
 
 int b200feat_version(void);
@@ -136,20 +137,28 @@ int64_t b200feat_num_frames(const b200feat_handle *h, int64_t num_samples);
 int32_t b200feat_feature_dim(const b200feat_handle *h);
 /* B200FEAT_KERNEL_GENERIC or B200FEAT_KERNEL_FAST — what AUTO resolved to. */
 int32_t b200feat_kernel_kind(const b200feat_handle *h);
-/* number of int64 words of batch metadata for B cuts */
+/* number of int64 words of the fixed part of the batch metadata for B cuts (4B + 2) */
 int64_t b200feat_meta_words(int32_t batch);
+/* exact number of int64 words b200feat_plan_batch writes for these cuts: the fixed part plus, for
+ * tiled kernels, one int32 per tile mapping the tile to its cut (so that the kernel needs one load,
+ * not a binary search, to locate its work).  Negative code on error (e.g. B200FEAT_ESHORT). */
+int64_t b200feat_plan_words(const b200feat_handle *h, const int64_t *num_samples, int32_t batch,
+                            int32_t out_mode);
 
 /*
  * Host-side batch planning (pure integer work, no CUDA).
  *   num_samples[B]     : length of every cut
  *   sample_offsets[B]  : element offset of every cut in the sample buffer, or NULL to pack the
  *                        cuts back to back with each start aligned to `align` elements
- *   meta_host          : out, b200feat_meta_words(B) int64 words; copy verbatim to the device
- * Layout of meta: [0,B) sample offsets | [B,2B) lengths | [2B,3B+1) row prefix | [3B+1,4B+2) tile prefix.
+ *   meta_host          : out, `meta_capacity` int64 words (>= b200feat_plan_words(...)); copy
+ *                        totals->meta_words words verbatim to the device
+ * Layout of meta: [0,B) sample offsets | [B,2B) lengths | [2B,3B+1) row prefix | [3B+1,4B+2) tile
+ * prefix | int32 tile->cut table (tiled kernels only).
  */
 int b200feat_plan_batch(const b200feat_handle *h, const int64_t *num_samples,
                         const int64_t *sample_offsets, int32_t batch, int32_t align,
-                        int32_t out_mode, int64_t *meta_host, b200feat_batch_totals *totals);
+                        int32_t out_mode, int64_t *meta_host, int64_t meta_capacity,
+                        b200feat_batch_totals *totals);
 
 /*
  * The hot call: device-resident ragged batch -> device-resident features.  Asynchronous on

@@ -288,13 +288,33 @@ int32_t b200feat_feature_dim(const b200feat_handle *h) { return h ? h->plan.F : 
 int32_t b200feat_kernel_kind(const b200feat_handle *h) { return h ? h->kernel : B200FEAT_EINVAL; }
 int64_t b200feat_meta_words(int32_t batch) { return 4 * (int64_t)batch + 2; }
 
+int64_t b200feat_plan_words(const b200feat_handle *hc, const int64_t *num_samples, int32_t B, int32_t out_mode) {
+  b200feat_handle *h = const_cast<b200feat_handle *>(hc);
+  if (!h || !num_samples || B <= 0) return fail(h, B200FEAT_EINVAL, "plan_words: bad arguments");
+  int64_t words = b200feat_meta_words(B);
+  const int64_t ft = h->frames_per_tile;
+  if (ft <= 1) return words;
+  int64_t tmax = 0, tiles = 0;
+  for (int i = 0; i < B; ++i) {
+    const int64_t T = frames_for(h->desc, num_samples[i]);
+    if (!framable(h->desc, num_samples[i], T))
+      return fail(h, B200FEAT_ESHORT, "cut " + std::to_string(i) + " with " + std::to_string(num_samples[i]) +
+                                          " samples is too short to be framed");
+    if (T > tmax) tmax = T;
+    tiles += (T + ft - 1) / ft;
+  }
+  if (out_mode == B200FEAT_OUT_PADDED) tiles = (int64_t)B * ((tmax + ft - 1) / ft);
+  return words + (tiles + 1) / 2;
+}
+
 int b200feat_plan_batch(const b200feat_handle *hc, const int64_t *num_samples,
                         const int64_t *sample_offsets, int32_t B, int32_t align, int32_t out_mode,
-                        int64_t *meta, b200feat_batch_totals *tot) {
+                        int64_t *meta, int64_t meta_capacity, b200feat_batch_totals *tot) {
   b200feat_handle *h = const_cast<b200feat_handle *>(hc);
   if (!h || !num_samples || !meta || !tot || B <= 0) return fail(h, B200FEAT_EINVAL, "plan_batch: bad arguments");
   if (out_mode != B200FEAT_OUT_PACKED && out_mode != B200FEAT_OUT_PADDED) return fail(h, B200FEAT_EINVAL, "bad out_mode");
   if (align < 1) align = 1;
+  if (meta_capacity < b200feat_meta_words(B)) return fail(h, B200FEAT_EINVAL, "plan_batch: meta buffer too small");
   int64_t *soff = meta, *ns = meta + B, *roff = meta + 2 * (int64_t)B, *toff = meta + 3 * (int64_t)B + 1;
   int64_t cur = 0, rows = 0, tmax = 0, span = 0;
   for (int i = 0; i < B; ++i) {
@@ -320,6 +340,16 @@ int b200feat_plan_batch(const b200feat_handle *hc, const int64_t *num_samples,
     tiles += (r + ft - 1) / ft;
   }
   toff[B] = tiles;
+  int64_t words = b200feat_meta_words(B);
+  if (ft > 1) {  // tile -> cut table for the tiled kernel
+    if (meta_capacity < words + (tiles + 1) / 2) return fail(h, B200FEAT_EINVAL, "plan_batch: meta buffer too small for the tile table");
+    int32_t *tc = reinterpret_cast<int32_t *>(meta + words);
+    for (int i = 0; i < B; ++i)
+      for (int64_t t = toff[i]; t < toff[i + 1]; ++t) tc[t] = i;
+    if (tiles & 1) tc[tiles] = 0;
+    words += (tiles + 1) / 2;
+  }
+  tot->meta_words = words;
   tot->total_rows = rows; tot->max_frames = tmax; tot->total_tiles = tiles; tot->span_samples = span;
   tot->out_floats = (out_mode == B200FEAT_OUT_PADDED ? (int64_t)B * tmax : rows) * h->plan.F;
   return B200FEAT_OK;
@@ -336,6 +366,7 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   db.nsamp = meta_dev + B + b0;
   db.row_off = meta_dev + 2 * (int64_t)B + b0;
   db.tile_off = meta_dev + 3 * (int64_t)B + 1 + b0;
+  db.tile_cut = h->frames_per_tile > 1 ? reinterpret_cast<const int32_t *>(meta_dev + 4 * (int64_t)B + 2) : nullptr;
   db.out = out_dev;
   db.tile_base = tile0;
   db.num_tiles = tile1 - tile0;
@@ -396,7 +427,8 @@ int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t 
   struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
 
   const size_t esz = dt == B200FEAT_I16 ? 2 : 4;
-  const int64_t words = b200feat_meta_words(B);
+  const int64_t words = b200feat_plan_words(h, num_samples, B, out_mode);
+  if (words < 0) return (int)words;
   if (r.h_meta_cap < (size_t)words) {
     if (r.h_meta) cudaFreeHost(r.h_meta);
     r.h_meta = nullptr; r.h_meta_cap = 0;
@@ -405,7 +437,7 @@ int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t 
   }
   b200feat_batch_totals tot;
   // host layout is back-to-back (align 1) so the user's buffer is copied verbatim
-  int rc = b200feat_plan_batch(h, num_samples, nullptr, B, 1, out_mode, r.h_meta, &tot);
+  int rc = b200feat_plan_batch(h, num_samples, nullptr, B, 1, out_mode, r.h_meta, words, &tot);
   if (rc) return rc;
   for (auto &s : r.streams) if (!s) CU_TRY(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   if (!r.meta_ready) CU_TRY(h, cudaEventCreateWithFlags(&r.meta_ready, cudaEventDisableTiming));

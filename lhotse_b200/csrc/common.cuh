@@ -35,6 +35,7 @@ struct DevBatch {
   const int64_t *nsamp;     // [B]
   const int64_t *row_off;   // [B+1] packed-row prefix (absolute rows)
   const int64_t *tile_off;  // [B+1] tile prefix (absolute)
+  const int32_t *tile_cut;  // [total tiles] absolute tile -> absolute cut (tiled kernels), or nullptr
   float *out;
   int64_t tile_base;    // first tile of this launch (absolute)
   int64_t num_tiles;    // tiles in this launch

@@ -14,6 +14,7 @@
 // :32-42 (_rfft/_pow_spectrogram), :565-578 (mel+log), :708-724 (DCT/lifter), with the framing of
 // :727-772 folded into the load addresses.  HBM traffic: 4*S bytes in, 4*F bytes out per frame.
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -24,15 +25,21 @@
 #define F512_TILE (F512_HW * F512_SLOTS)    // frames per tile (64)
 #define F512_XROW 18                        // float2 per transpose row (16 + 2 pad: 144 B, LDS.128 conflict-free)
 #define F512_XBUF (16 * F512_XROW)          // float2 per half-warp transpose tile
-#define F512_PBINS 260                      // bins per P tile (257 rounded up)
-#define F512_PBUF (F512_PBINS * F512_SLOTS) // floats per half-warp P tile
+#define F512_PBINS 260                      // floats per P row (257 bins; 4*260 = 16 mod 32 keeps the two half-warps of a
+                                            // warp on disjoint banks when they store the same bin of their frames)
+#define F512_PBUF (F512_PBINS * F512_SLOTS) // floats per half-warp P tile, laid out [slot][bin]
+#define F512_PTAIL 64                       // zeroed slack after the last tile (mel reads run past short filters)
 
 struct Fast512Tables {  // device pointers, derived once per handle
   const float2 *win2;   // [16][16] window pairs (w[32*n1+2l], w[32*n1+2l+1]), zero beyond L
   const float2 *tw1;    // [16][16] W256^(l*k1) indexed [k1][l]
   const float2 *w512;   // [16]     W512^l
-  int mel_nnz;          // floats in mel_w
+  const int *rstart;    // [rounds][16] first FFT bin of filter m = lane + 16*round (0 if m >= M)
+  const int *rlen;      // [rounds]     trip count of the round = its longest filter
+  const int *rrow;      // [rounds]     first row of the round in wdense
+  const float *wdense;  // [rows][16]   weights, zero-padded to the round's trip count
   int mel_rounds;       // ceil(M / 16)
+  int mel_wrows;        // sum of rlen
 };
 
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -104,18 +111,24 @@ __device__ __forceinline__ float2 ld_pair(const void *base, int64_t i) {  // i e
   }
 }
 
-// The two half-warps of a warp run independent frames (and may diverge at cut edges), so every
-// warp-level primitive below is scoped to the calling half with `hmask`.
-__device__ __forceinline__ float hw_sum(float v, unsigned hmask) {  // sum over the 16 lanes of a half-warp
+// The two half-warps of a warp process different frames but execute in LOCKSTEP: every branch below
+// is warp-uniform (decided with __any_sync/__all_sync), so the full-mask shuffles (width 16) and
+// __syncwarp() compile to single instructions (a runtime half-mask costs a MATCH/REDUX/VOTE
+// sequence per shuffle).  A half whose frame lies beyond its cut recomputes the cut's last frame
+// and simply does not store it.
+#define F512_FULL 0xffffffffu
+__device__ __forceinline__ float hw_sum(float v) {  // sum over the 16 lanes of each half-warp
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(hmask, v, o);
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(F512_FULL, v, o, 16);
   return v;
 }
 
 static inline size_t fast512_smem_bytes(const DevPlan &p, const Fast512Tables &t) {
-  size_t b = (size_t)F512_HW * (F512_XBUF * 8 + F512_PBUF * 4);
-  b += 16 * 16 * 8;                          // window pairs
-  b += (size_t)p.M * 3 * 4 + (size_t)t.mel_nnz * 4;  // mel start/len/woff + weights
+  size_t b = (size_t)F512_HW * (F512_XBUF * 8 + F512_PBUF * 4) + F512_PTAIL * 4;
+  b += 16 * 16 * 8;                                   // window pairs
+  b += (size_t)t.mel_rounds * 16 * 4 * 2;             // per-round per-lane first bin + output filter
+  b += (size_t)t.mel_rounds * 4;                      // per-round trip count
+  b += (size_t)t.mel_wrows * 16 * 4;                  // dense zero-padded weights [row][lane]
   return (b + 15) & ~(size_t)15;
 }
 
@@ -126,28 +139,26 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   const int tid = threadIdx.x;
   const int l = tid & 15;           // lane within the half-warp
   const int hw = tid >> 4;          // half-warp within the CTA
-  const unsigned hmask = (tid & 16) ? 0xffff0000u : 0x0000ffffu;
   const int L = LCT ? LCT : p.L;
   constexpr int NP = LCT ? (LCT + 31) / 32 : 16;  // sample-pair registers actually needed
 
   // ---- shared memory carve-up
   float2 *xall = reinterpret_cast<float2 *>(smem_raw);
   float *pall = reinterpret_cast<float *>(xall + (size_t)F512_HW * F512_XBUF);
-  float2 *s_win = reinterpret_cast<float2 *>(pall + (size_t)F512_HW * F512_PBUF);
-  int *s_mstart = reinterpret_cast<int *>(s_win + 256);
-  int *s_mlen = s_mstart + p.M;
-  int *s_mwoff = s_mlen + p.M;
-  float *s_mw = reinterpret_cast<float *>(s_mwoff + p.M);
+  float2 *s_win = reinterpret_cast<float2 *>(pall + (size_t)F512_HW * F512_PBUF + F512_PTAIL);
+  int *s_rstart = reinterpret_cast<int *>(s_win + 256);       // [round][lane] first bin of the lane's filter
+  int *s_rlen = s_rstart + ft.mel_rounds * 16;                // [round] trip count (longest filter of the round)
+  int *s_rrow = s_rlen + ft.mel_rounds;                       // [round] first weight row
+  float *s_mw = reinterpret_cast<float *>(s_rrow + ft.mel_rounds);  // [row][lane] zero-padded weights
   float2 *X = xall + (size_t)hw * F512_XBUF;
-  float *P = pall + (size_t)hw * F512_PBUF;
+  float *P = pall + (size_t)hw * F512_PBUF;                   // [slot][F512_PBINS]
 
   for (int i = tid; i < 256; i += blockDim.x) s_win[i] = __ldg(ft.win2 + i);
-  for (int i = tid; i < p.M; i += blockDim.x) {
-    s_mstart[i] = __ldg(p.mel_start + i);
-    s_mlen[i] = __ldg(p.mel_len + i);
-    s_mwoff[i] = __ldg(p.mel_woff + i);
-  }
-  for (int i = tid; i < ft.mel_nnz; i += blockDim.x) s_mw[i] = __ldg(p.mel_w + i);
+  for (int i = tid; i < ft.mel_rounds * 16; i += blockDim.x) s_rstart[i] = __ldg(ft.rstart + i);
+  for (int i = tid; i < ft.mel_rounds; i += blockDim.x) { s_rlen[i] = __ldg(ft.rlen + i); s_rrow[i] = __ldg(ft.rrow + i); }
+  for (int i = tid; i < ft.mel_wrows * 16; i += blockDim.x) s_mw[i] = __ldg(ft.wdense + i);
+  // P is read past a filter's support with zero weights: it must never hold NaN patterns
+  for (int i = tid; i < F512_HW * F512_PBUF + F512_PTAIL; i += blockDim.x) pall[i] = 0.f;
 
   // per-lane constants kept in registers for the whole kernel
   float2 tw1[16];
@@ -160,11 +171,11 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 
   for (int64_t tg = blockIdx.x; tg < b.num_tiles; tg += gridDim.x) {
     const int64_t tile = b.tile_base + tg;
-    const int cut = find_segment(b.tile_off, b.B, tile);
+    const int cut = __ldg(b.tile_cut + tile) - b.batch_first;  // host-built tile->cut table: one load, no search
     const int64_t t0 = (tile - __ldg(b.tile_off + cut)) * F512_TILE + (int64_t)hw * F512_SLOTS;
     const int64_t T = __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut);
     const int64_t rows_here = b.out_mode == B200FEAT_OUT_PADDED ? b.max_frames : T;
-    if (t0 >= rows_here) continue;  // whole half-warp idle for this tile (warp-divergent at most by halves)
+    if (!__any_sync(F512_FULL, t0 < rows_here)) continue;  // both halves idle for this tile
     const int64_t n = __ldg(b.nsamp + cut);
     const int64_t xoff = __ldg(b.samp_off + cut);
     const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED
@@ -174,32 +185,42 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 
 #pragma unroll 1
     for (int f = 0; f < F512_SLOTS; ++f) {
-      const int64_t t = t0 + f;
       le[f] = 0.f;
-      if (t >= T) {  // beyond the cut: zero the P column so the mel phase stays finite
-        for (int k = l; k < F512_PBINS; k += 16) P[k * F512_SLOTS + f] = 0.f;
-        continue;
-      }
+      if (!__any_sync(F512_FULL, t0 + f < T)) continue;    // neither half has a frame in this slot
+      const int64_t t = min(t0 + f, T - 1);                // an out-of-range half redoes the last frame (not stored)
       const int64_t base = t * p.S - (p.snip_edges ? 0 : p.pad_left);
       float2 v[16];
       float prev[NP];
       const bool interior = base >= 0 && base + L <= n && (((xoff + base) & 1) == 0);
-      if (interior) {
+      if (__all_sync(F512_FULL, interior)) {
+        if (DT == B200FEAT_I16) {
+          const int16_t *xp = reinterpret_cast<const int16_t *>(b.samples) + (xoff + base + 2 * l);
 #pragma unroll
-        for (int n1 = 0; n1 < NP; ++n1) {
-          const int j0 = 32 * n1 + 2 * l;
-          if (j0 + 1 < L) {
-            v[n1] = ld_pair<DT>(b.samples, xoff + base + j0);
-            prev[n1] = ld_sample<DT>(b.samples, xoff + base + (j0 > 0 ? j0 - 1 : 0));
-          } else if (j0 < L) {  // odd L: last tap alone
-            v[n1] = make_float2(ld_sample<DT>(b.samples, xoff + base + j0), 0.f);
-            prev[n1] = ld_sample<DT>(b.samples, xoff + base + (j0 > 0 ? j0 - 1 : 0));
-          } else {
+          for (int n1 = 0; n1 < NP; ++n1) {
+            const int j0 = 32 * n1 + 2 * l;
             v[n1] = make_float2(0.f, 0.f);
             prev[n1] = 0.f;
+            if (j0 + 1 < L) {
+              const short2 q = __ldg(reinterpret_cast<const short2 *>(xp + 32 * n1));
+              v[n1] = make_float2((float)q.x * (1.0f / 32768.0f), (float)q.y * (1.0f / 32768.0f));
+            } else if (j0 < L) {
+              v[n1].x = (float)__ldg(xp + 32 * n1) * (1.0f / 32768.0f);
+            }
+            if (j0 < L) prev[n1] = (float)__ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0)) * (1.0f / 32768.0f);
+          }
+        } else {
+          const float *xp = reinterpret_cast<const float *>(b.samples) + (xoff + base + 2 * l);
+#pragma unroll
+          for (int n1 = 0; n1 < NP; ++n1) {
+            const int j0 = 32 * n1 + 2 * l;
+            v[n1] = make_float2(0.f, 0.f);
+            prev[n1] = 0.f;
+            if (j0 + 1 < L) v[n1] = __ldg(reinterpret_cast<const float2 *>(xp + 32 * n1));
+            else if (j0 < L) v[n1].x = __ldg(xp + 32 * n1);  // odd L: last tap alone
+            if (j0 < L) prev[n1] = __ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0));
           }
         }
-      } else {  // edge frame: per-tap reflection (layers.py:753-772); ~3 frames per cut
+      } else {  // a cut edge in this warp: per-tap reflection (layers.py:753-772); ~3 frames per cut
 #pragma unroll
         for (int n1 = 0; n1 < NP; ++n1) {
           const int j0 = 32 * n1 + 2 * l;
@@ -225,7 +246,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       float s = 0.f;
 #pragma unroll
       for (int n1 = 0; n1 < NP; ++n1) s += v[n1].x + v[n1].y;  // taps beyond L are exact zeros
-      const float mu = p.remove_dc ? hw_sum(s, hmask) * inv_L : 0.f;
+      const float mu = p.remove_dc ? hw_sum(s) * inv_L : 0.f;
       // ---- energy, pre-emphasis, window (layers.py:159-170); zero padding is implicit
       float e = 0.f;
 #pragma unroll
@@ -245,7 +266,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           v[n1] = make_float2(0.f, 0.f);
         }
       }
-      if (p.use_energy) le[f] = log_energy_value(p, hw_sum(e, hmask));
+      if (p.use_energy) le[f] = log_energy_value(p, hw_sum(e));
 
       // ---- stage 1: radix-16 over n1, twiddle, transpose
       dft16(v);
@@ -255,7 +276,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         if (k1 > 0) y = f2mul(y, tw1[k1]);
         X[k1 * F512_XROW + l] = y;
       }
-      __syncwarp(hmask);
+      __syncwarp();
       {
         const float4 *row = reinterpret_cast<const float4 *>(X + l * F512_XROW);
 #pragma unroll
@@ -265,46 +286,62 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           v[2 * q + 1] = make_float2(r.z, r.w);
         }
       }
-      __syncwarp(hmask);
+      __syncwarp();
       // ---- stage 2: radix-16 over n2 -> Z[l + 16*k2]
       dft16(v);
-      // ---- real-FFT split + power (layers.py:38-42): X[k] = 0.5*(E - i*W512^k*O)
+      // ---- real-FFT split + power (layers.py:38-42).  With E = Z[k] + conj(Z[256-k]), O = Z[k] - conj(Z[256-k]),
+      // T = W512^k * O:   2*X[k] = E - i*T   and   2*conj(X[256-k]) = E + i*T, so one (E, O, T) serves two bins.
+      // Lane l owns k = l + 16*k2 and its mirror lane 16-l owns 256-k: each lane handles its EVEN k2 and gets
+      // the mirror's ODD slots (8 complex shuffles instead of 16).  Lane 0 mirrors itself with a one-slot
+      // shift (256 - 16*j = 16*(16-j)), so it walks the pairs (0,0) (2,14) (4,12) (6,10) (8,8) (1,15) (3,13) (5,11)
+      // here and (7,9) below.  The 1/4 of |X|^2 = |2X|^2/4 is folded into the mel weights / spectrogram epilogue.
+      float *Pf = P + f * F512_PBINS;
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) {
-        const float2 zk = v[F512_OUT(k2)];
-        // what my mirror lane needs from me at this step: Z[.. 15-k2] (lane 0 mirrors itself, shifted by one)
-        const float2 za = v[F512_OUT(15 - k2)];
-        const float2 zb = v[F512_OUT((16 - k2) & 15)];
-        const float sx = l == 0 ? zb.x : za.x;
-        const float sy = l == 0 ? zb.y : za.y;
-        const float cx = __shfl_sync(hmask, sx, partner, 16);
-        const float cy = __shfl_sync(hmask, sy, partner, 16);
-        const float er = zk.x + cx, ei = zk.y - cy;   // E = Zk + conj(Zc)
-        const float orr = zk.x - cx, oi = zk.y + cy;  // O = Zk - conj(Zc)
-        const float2 u = f2mul(make_float2(orr, oi), w32_const(k2));
-        const float2 tt = f2mul(u, w512l);
-        const float xr = er + tt.y, xi = ei - tt.x;   // 2*X[k]
-        float pw = 0.25f * fmaf(xr, xr, xi * xi);
-        if (p.use_mag) pw = sqrtf(pw);
-        P[(l + 16 * k2) * F512_SLOTS + f] = pw;
-        if (k2 == 0 && l == 0) {  // Nyquist bin: X[256] = Re Z0 - Im Z0
-          const float xn = zk.x - zk.y;
-          P[256 * F512_SLOTS + f] = p.use_mag ? fabsf(xn) : xn * xn;
-        }
+      for (int i = 0; i < 8; ++i) {
+        constexpr int kOwn0[8] = {0, 2, 4, 6, 8, 1, 3, 5};
+        constexpr int kSend0[8] = {0, 14, 12, 10, 8, 15, 13, 11};
+        const float2 zo = v[F512_OUT(2 * i)], zo0 = v[F512_OUT(kOwn0[i])];
+        const float2 zs = v[F512_OUT(15 - 2 * i)], zs0 = v[F512_OUT(kSend0[i])];
+        const float2 zk = (i >= 5 && l == 0) ? zo0 : zo;
+        const float sx = l == 0 ? zs0.x : zs.x, sy = l == 0 ? zs0.y : zs.y;
+        const float cx = __shfl_sync(F512_FULL, sx, partner, 16);
+        const float cy = __shfl_sync(F512_FULL, sy, partner, 16);
+        const float er = zk.x + cx, ei = zk.y - cy;   // E
+        const float orr = zk.x - cx, oi = zk.y + cy;  // O
+        float2 wc = w32_const(2 * i);                 // W16^i; lane 0 needs W32^(own slot)
+        if (i >= 5) { const float2 w0 = w32_const(kOwn0[i]); wc = l == 0 ? w0 : wc; }
+        const float2 tt = f2mul(f2mul(make_float2(orr, oi), wc), w512l);
+        const float ar = er + tt.y, ai = ei - tt.x;   // 2*X[k]
+        const float br = er - tt.y, bi = ei + tt.x;   // 2*conj(X[256-k])
+        float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+        if (p.use_mag) { pa = sqrtf(pa); pb = sqrtf(pb); }
+        const int k = l == 0 ? 16 * kOwn0[i] : l + 32 * i;
+        Pf[k] = pa;
+        Pf[256 - k] = pb;
+      }
+      if (l == 0) {  // lane 0's last pair: slots (7, 9) -> bins 112 and 144
+        const float2 zk = v[F512_OUT(7)], zc = v[F512_OUT(9)];
+        const float er = zk.x + zc.x, ei = zk.y - zc.y, orr = zk.x - zc.x, oi = zk.y + zc.y;
+        const float2 tt = f2mul(make_float2(orr, oi), w32_const(7));
+        const float ar = er + tt.y, ai = ei - tt.x, br = er - tt.y, bi = ei + tt.x;
+        float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+        if (p.use_mag) { pa = sqrtf(pa); pb = sqrtf(pb); }
+        Pf[112] = pa;
+        Pf[144] = pb;
       }
     }
-    __syncwarp(hmask);
+    __syncwarp();
 
     // ---- epilogue over the (up to) 4 frames of this half-warp
-    const int nvalid = (int)min((int64_t)F512_SLOTS, T - t0) < 0 ? 0 : (int)min((int64_t)F512_SLOTS, T - t0);
-    const int nrows = (int)min((int64_t)F512_SLOTS, rows_here - t0);
+    const int nvalid = (int)max((int64_t)0, min((int64_t)F512_SLOTS, T - t0));
+    const int nrows = (int)max((int64_t)0, min((int64_t)F512_SLOTS, rows_here - t0));
     float *out = b.out + row0 * p.F;
     if (p.feature == B200FEAT_SPECTROGRAM || p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int f = 0; f < nrows; ++f) {
         float *o = out + (int64_t)f * p.F;
         if (f >= nvalid) { for (int k = l; k < p.F; k += 16) o[k] = b.pad_value; continue; }
         for (int k = l; k < p.K; k += 16) {
-          float x = P[k * F512_SLOTS + f];
+          float x = P[f * F512_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);  // P holds |2X|^2 (or |2X|)
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
           if (k == 0 && p.use_energy) x = le[f];
           o[k] = x;
@@ -316,20 +353,21 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       float *mlog = reinterpret_cast<float *>(X);  // the transpose tile is idle during the epilogue
       for (int j = 0; j < ft.mel_rounds; ++j) {
         const int m = l + 16 * j;
-        const bool mv = m < p.M;
-        const int st = mv ? s_mstart[m] : 0, len = mv ? s_mlen[m] : 0;
-        const float *w = s_mw + (mv ? s_mwoff[m] : 0);
-        const float4 *P4 = reinterpret_cast<const float4 *>(P) + st;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float *Pj = P + s_rstart[j * 16 + l];
+        const float *wj = s_mw + s_rrow[j] * 16 + l;
+        const int len = s_rlen[j];  // uniform: shorter filters continue on zero weights
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
         for (int i = 0; i < len; ++i) {
-          const float wi = w[i];
-          const float4 pv = P4[i];
-          acc.x = fmaf(pv.x, wi, acc.x); acc.y = fmaf(pv.y, wi, acc.y);
-          acc.z = fmaf(pv.z, wi, acc.z); acc.w = fmaf(pv.w, wi, acc.w);
+          const float wi = wj[i * 16];
+          a0 = fmaf(Pj[i], wi, a0);
+          a1 = fmaf(Pj[F512_PBINS + i], wi, a1);
+          a2 = fmaf(Pj[2 * F512_PBINS + i], wi, a2);
+          a3 = fmaf(Pj[3 * F512_PBINS + i], wi, a3);
         }
-        if (mv) {
-          const float r[4] = {logf(fmaxf(acc.x, p.mel_floor)), logf(fmaxf(acc.y, p.mel_floor)),
-                              logf(fmaxf(acc.z, p.mel_floor)), logf(fmaxf(acc.w, p.mel_floor))};
+        if (m < p.M) {
+          const float r[4] = {__logf(fmaxf(a0, p.mel_floor)), __logf(fmaxf(a1, p.mel_floor)),
+                              __logf(fmaxf(a2, p.mel_floor)), __logf(fmaxf(a3, p.mel_floor))};
           if (p.feature == B200FEAT_FBANK) {
 #pragma unroll
             for (int f = 0; f < F512_SLOTS; ++f)
@@ -343,7 +381,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       if (p.feature == B200FEAT_FBANK) {
         if (shift && l < nvalid) out[(int64_t)l * p.F] = le[0] * (l == 0) + le[1] * (l == 1) + le[2] * (l == 2) + le[3] * (l == 3);
       } else {
-        __syncwarp(hmask);
+        __syncwarp();
         for (int idx = l; idx < nvalid * p.C; idx += 16) {
           const int f = idx / p.C, c = idx - f * p.C;
           float acc = 0.f;
@@ -357,7 +395,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       for (int f = nvalid; f < nrows; ++f)
         for (int k = l; k < p.F; k += 16) out[(int64_t)f * p.F + k] = b.pad_value;
     }
-    __syncwarp(hmask);
+    __syncwarp();
   }
 }
 
@@ -410,15 +448,44 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   if ((rc = f512_upload(win2, allocs, &hst.t.win2))) return rc;
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
-  int nnz = 0;  // must match the packing of mel_w in b200feat_create (0 when there is no bank)
-  for (int m = 0; m < p.M; ++m) {
-    int first = -1, last = -1;
-    for (int k = 0; k < p.K; ++k)
-      if (bank[(size_t)k * p.M + m] != 0.f) { if (first < 0) first = k; last = k; }
-    if (first >= 0) nnz += last - first + 1;
+  // mel bank re-packed for the epilogue: round j serves filters 16j..16j+15 (one per lane) with a common
+  // trip count; weights beyond a filter's support are zero
+  const int rounds = (p.M + 15) / 16;
+  const float pscale = p.use_mag ? 0.5f : 0.25f;  // the kernel stores |2X|^2 (or |2X|); exact power-of-two rescale
+  std::vector<int> rstart(std::max(rounds, 1) * 16, 0), rlen(std::max(rounds, 1), 0), rrow(std::max(rounds, 1), 0);
+  std::vector<float> wdense;
+  for (int j = 0; j < rounds; ++j) {
+    int first[16], len[16], mx = 0;
+    for (int l = 0; l < 16; ++l) {
+      const int m = l + 16 * j;
+      first[l] = 0; len[l] = 0;
+      if (m < p.M) {
+        int f0 = -1, f1 = -1;
+        for (int k = 0; k < p.K; ++k)
+          if (bank[(size_t)k * p.M + m] != 0.f) { if (f0 < 0) f0 = k; f1 = k; }
+        if (f0 >= 0) { first[l] = f0; len[l] = f1 - f0 + 1; }
+      }
+      if (len[l] > mx) mx = len[l];
+      rstart[j * 16 + l] = first[l];
+    }
+    if (mx > F512_PTAIL) return B200FEAT_EUNSUPPORTED;  // a filter wider than the zeroed slack
+    for (int l = 0; l < 16; ++l)  // zero-weight over-reads must stay inside the frame's own P row
+      if (first[l] + mx > F512_PBINS) return B200FEAT_EUNSUPPORTED;
+    rlen[j] = mx;
+    rrow[j] = (int)(wdense.size() / 16);
+    for (int i = 0; i < mx; ++i)
+      for (int l = 0; l < 16; ++l) {
+        const int m = l + 16 * j;
+        wdense.push_back((m < p.M && i < len[l]) ? pscale * bank[(size_t)(first[l] + i) * p.M + m] : 0.f);
+      }
   }
-  hst.t.mel_nnz = nnz;
-  hst.t.mel_rounds = (p.M + 15) / 16;
+  if (wdense.empty()) wdense.assign(16, 0.f);
+  if ((rc = f512_upload(rstart, allocs, &hst.t.rstart))) return rc;
+  if ((rc = f512_upload(rlen, allocs, &hst.t.rlen))) return rc;
+  if ((rc = f512_upload(rrow, allocs, &hst.t.rrow))) return rc;
+  if ((rc = f512_upload(wdense, allocs, &hst.t.wdense))) return rc;
+  hst.t.mel_rounds = rounds;
+  hst.t.mel_wrows = rounds ? (int)(wdense.size() / 16) : 0;
   hst.smem = fast512_smem_bytes(p, hst.t);
   if (hst.smem > 113 * 1024) return B200FEAT_EUNSUPPORTED;  // keep 2 CTAs per SM
   if (f512_set_attr<B200FEAT_F32, 400>(hst.smem) || f512_set_attr<B200FEAT_I16, 400>(hst.smem) ||

@@ -48,7 +48,7 @@ class PlanDesc(C.Structure):
 
 class BatchTotals(C.Structure):
     _fields_ = [("total_rows", C.c_int64), ("max_frames", C.c_int64), ("total_tiles", C.c_int64),
-                ("span_samples", C.c_int64), ("out_floats", C.c_int64)]
+                ("span_samples", C.c_int64), ("out_floats", C.c_int64), ("meta_words", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -59,7 +59,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "b200feat_version", "b200feat_global_error", "b200feat_create", "b200feat_destroy",
     "b200feat_last_error", "b200feat_num_frames", "b200feat_feature_dim", "b200feat_kernel_kind",
-    "b200feat_meta_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
+    "b200feat_meta_words", "b200feat_plan_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
     "b200feat_get_table", "b200feat_get_stats",
 ]
 
@@ -99,8 +99,10 @@ def load_library():
         lib.b200feat_kernel_kind.argtypes = [vp]
         lib.b200feat_meta_words.restype = i64
         lib.b200feat_meta_words.argtypes = [i32]
+        lib.b200feat_plan_words.restype = i64
+        lib.b200feat_plan_words.argtypes = [vp, vp, i32, i32]
         lib.b200feat_plan_batch.restype = C.c_int
-        lib.b200feat_plan_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, C.POINTER(BatchTotals)]
+        lib.b200feat_plan_batch.argtypes = [vp, vp, vp, i32, i32, i32, vp, i64, C.POINTER(BatchTotals)]
         lib.b200feat_extract.restype = C.c_int
         lib.b200feat_extract.argtypes = [vp, vp, i32, vp, i32, C.POINTER(BatchTotals), vp, i32, C.c_float, vp]
         lib.b200feat_extract_host.restype = C.c_int
@@ -184,13 +186,18 @@ class Engine:
         B = len(num_samples)
         ns = np.ascontiguousarray(num_samples, dtype=np.int64)
         off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
-        meta = np.empty(int(self.lib.b200feat_meta_words(B)), dtype=np.int64)
+        words = int(self.lib.b200feat_plan_words(self._h, _ptr(ns), B, out_mode))
+        if words == -5:
+            raise ValueError(self.lib.b200feat_last_error(self._h).decode())
+        if words < 0:
+            self._check(words)
+        meta = np.empty(words, dtype=np.int64)
         tot = BatchTotals()
-        rc = self.lib.b200feat_plan_batch(self._h, _ptr(ns), _ptr(off), B, align, out_mode, _ptr(meta), C.byref(tot))
+        rc = self.lib.b200feat_plan_batch(self._h, _ptr(ns), _ptr(off), B, align, out_mode, _ptr(meta), words, C.byref(tot))
         if rc == -5:
             raise ValueError(self.lib.b200feat_last_error(self._h).decode())
         self._check(rc)
-        return meta, tot
+        return meta[: tot.meta_words], tot
 
     # ------------------------------------------------------------------ device-resident path
     def extract_device(self, samples: torch.Tensor, num_samples: Sequence[int],

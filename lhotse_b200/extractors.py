@@ -245,6 +245,27 @@ class _B200Extractor(FeatureExtractor):
             out, prefix = eng.extract_device(buf, lens, offsets=[i * nmax for i in range(B)])
             result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
             input_is_torch = True
+        elif isinstance(samples, torch.Tensor) and samples.ndim == 2:
+            # (B, n) tensor: the rows are the ragged buffer already (offset i*n) — no packing, no copies
+            B, nmax = samples.shape
+            buf = samples.contiguous()
+            if buf.dtype not in (torch.float32, torch.int16):
+                buf = buf.to(torch.float32)
+            buf = buf.to(eng.device, non_blocking=True).reshape(-1)
+            lens = [nmax] * B
+            out, prefix = eng.extract_device(buf, lens, offsets=[i * nmax for i in range(B)])
+            result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
+            input_is_torch = True
+        elif isinstance(samples, np.ndarray) and samples.ndim == 2:
+            # (B, n) array: handed to the C ABI host path as is (rows are back to back)
+            B, nmax = samples.shape
+            arr = np.ascontiguousarray(samples)
+            if arr.dtype not in (np.float32, np.int16):
+                arr = arr.astype(np.float32)
+            lens = [nmax] * B
+            out, prefix = eng.extract_host(arr.reshape(-1), lens)
+            result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
+            input_is_torch = False
         else:
             if isinstance(samples, (list, tuple)):
                 input_is_list = True

@@ -20,7 +20,7 @@ def declared_symbols():
 def test_header_symbols_are_exported():
     lib = ctypes.CDLL(engine.lib_path())
     syms = declared_symbols()
-    assert len(syms) >= 14
+    assert len(syms) >= 15
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/b200feat.h but not exported"
     assert sorted(engine.EXPORTS) == syms
@@ -30,7 +30,7 @@ def test_version_and_struct_layout():
     lib = engine.load_library()
     assert lib.b200feat_version() == 1
     assert ctypes.sizeof(engine.PlanDesc) == 16 * 4 + 4 * 4
-    assert ctypes.sizeof(engine.BatchTotals) == 5 * 8
+    assert ctypes.sizeof(engine.BatchTotals) == 6 * 8
     assert lib.b200feat_meta_words(10) == 42
 
 
