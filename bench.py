@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=2048, help="cuts per GPU per step")
     ap.add_argument("--cut-seconds", type=float, default=10.0)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "fast", "generic"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fast", "fast_x2", "generic"])
     ap.add_argument("--e2e-batch", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-cuts-per-worker", type=int, default=200)

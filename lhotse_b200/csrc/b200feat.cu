@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "generic.cuh"
 #include "fast512.cuh"
+#include "fast512x2.cuh"
 
 namespace {
 
@@ -46,6 +47,7 @@ struct b200feat_handle {
   std::mutex stats_mu;
   HostRing ring;
   Fast512Host fast;
+  FastX2Host fastx2;
 };
 
 namespace {
@@ -216,12 +218,15 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   if (desc->use_lifter) UP(upload(h, h->h_lifter.data(), h->h_lifter.size(), &p.lifter));
 
   // ---- kernel selection
-  const bool fast_ok = fast512_supported(p);
-  if (desc->kernel == B200FEAT_KERNEL_FAST && !fast_ok) {
+  const bool fast_ok = fastx2_supported(p) && fast512_supported(p);
+  const bool want_fast = desc->kernel == B200FEAT_KERNEL_FAST || desc->kernel == B200FEAT_KERNEL_FAST_X2;
+  if (want_fast && !fast_ok) {
     cudaSetDevice(prev); b200feat_destroy(h);
-    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernel requires N=512, L<=512 even S, fbank/mfcc/spectrogram kinds");
+    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 512 (256 < L <= 512)");
   }
-  h->kernel = (desc->kernel == B200FEAT_KERNEL_GENERIC || !fast_ok) ? B200FEAT_KERNEL_GENERIC : B200FEAT_KERNEL_FAST;
+  if (desc->kernel == B200FEAT_KERNEL_GENERIC || !fast_ok) h->kernel = B200FEAT_KERNEL_GENERIC;
+  else if (desc->kernel == B200FEAT_KERNEL_FAST_X2) h->kernel = B200FEAT_KERNEL_FAST_X2;
+  else h->kernel = B200FEAT_KERNEL_FAST;  // AUTO: the scalar kernel is the faster one today (profiles/README.md)
 
   {  // generic launch shape: as many warps per CTA as fit ~100 KB, CTA <= 8 warps
     const size_t per_warp = generic_smem_per_warp(p.N, p.Nc);
@@ -244,8 +249,10 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
     }
   }
   h->frames_per_tile = 1;
-  if (h->kernel == B200FEAT_KERNEL_FAST) {
-    rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
+  if (h->kernel != B200FEAT_KERNEL_GENERIC) {
+    rc = h->kernel == B200FEAT_KERNEL_FAST_X2
+             ? fastx2_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fastx2)
+             : fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
     if (rc == B200FEAT_EUNSUPPORTED && desc->kernel == B200FEAT_KERNEL_AUTO) {
       h->kernel = B200FEAT_KERNEL_GENERIC;  // e.g. the plan's tables do not fit the fast kernel's shared memory
       h->frames_per_tile = 1;
@@ -376,7 +383,10 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   db.out_mode = out_mode;
   db.pad_value = pad_value;
   if (db.num_tiles <= 0) return 0;
-  if (h->kernel == B200FEAT_KERNEL_FAST) {
+  if (h->kernel == B200FEAT_KERNEL_FAST_X2) {
+    int rc = fastx2_launch(h->plan, h->fastx2, db, dt, h->sm_count, stream);
+    if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512x2 launch: ") + cudaGetErrorString((cudaError_t)rc));
+  } else if (h->kernel == B200FEAT_KERNEL_FAST) {
     int rc = fast512_launch(h->plan, h->fast, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512 launch: ") + cudaGetErrorString((cudaError_t)rc));
   } else {

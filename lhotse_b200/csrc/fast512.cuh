@@ -28,6 +28,9 @@
 #define F512_PBINS 260                      // floats per P row (257 bins; 4*260 = 16 mod 32 keeps the two half-warps of a
                                             // warp on disjoint banks when they store the same bin of their frames)
 #define F512_PBUF (F512_PBINS * F512_SLOTS) // floats per half-warp P tile, laid out [slot][bin]
+#ifndef F512_PREFETCH
+#define F512_PREFETCH 1
+#endif
 #define F512_PTAIL 64                       // zeroed slack after the last tile (mel reads run past short filters)
 
 struct Fast512Tables {  // device pointers, derived once per handle
@@ -192,6 +195,13 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       float2 v[16];
       float prev[NP];
       const bool interior = base >= 0 && base + L <= n && (((xoff + base) & 1) == 0);
+      if (F512_PREFETCH && l < 6) {  // the S new samples of the next frame: pull their lines towards L1 now
+        const int64_t nx = base + L + 32 * l;
+        if (nx >= 0 && nx + 32 <= n) {
+          const char *pp = reinterpret_cast<const char *>(b.samples) + (xoff + nx) * (DT == B200FEAT_I16 ? 2 : 4);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+        }
+      }
       if (__all_sync(F512_FULL, interior)) {
         if (DT == B200FEAT_I16) {
           const int16_t *xp = reinterpret_cast<const int16_t *>(b.samples) + (xoff + base + 2 * l);

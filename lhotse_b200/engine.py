@@ -24,8 +24,8 @@ _LIB_LOCK = threading.Lock()
 
 OUT_PACKED, OUT_PADDED = 0, 1
 DT_F32, DT_I16 = 0, 1
-KERNELS = {"auto": 0, "generic": 1, "fast": 2}
-KERNEL_NAMES = {1: "generic", 2: "fast"}
+KERNELS = {"auto": 0, "generic": 1, "fast": 2, "fast_x2": 3}
+KERNEL_NAMES = {1: "generic", 2: "fast", 3: "fast_x2"}
 
 
 class B200FeatError(RuntimeError):

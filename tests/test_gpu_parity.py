@@ -26,7 +26,7 @@ def make(feature, cfg, kernel="auto"):
     try:
         ext.engine
     except B200FeatError as e:
-        if e.code == -2 and kernel == "fast":
+        if e.code == -2 and kernel.startswith("fast"):
             pytest.skip("plan not supported by the fast kernel")
         raise
     return ext
@@ -34,7 +34,7 @@ def make(feature, cfg, kernel="auto"):
 
 def kernels_for(ext):
     """Every kernel that supports the plan is tested (generic always; fast when AUTO picks it)."""
-    return ["generic"] if ext.engine.kernel == "generic" else ["generic", "fast"]
+    return ["generic"] if ext.engine.kernel == "generic" else ["generic", "fast", "fast_x2"]
 
 
 @pytest.mark.parametrize("i,c,x,y", GOLD, ids=IDS)
@@ -49,7 +49,7 @@ def test_golden_vectors(i, c, x, y):
         assert ok, f"kernel={k}: {msg}"
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("kernel", ["generic", "fast", "fast_x2"])
 def test_ragged_batch_equals_per_cut(kernel):
     rs = np.random.RandomState(5)
     lens = [159, 160, 1599, 16000, 16001, 23456, 480, 100000, 16080]
@@ -71,7 +71,7 @@ def test_ragged_batch_equals_per_cut(kernel):
         assert b.is_cuda and np.array_equal(a, b.cpu().numpy())
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("kernel", ["generic", "fast", "fast_x2"])
 def test_padded_mode_and_int16(kernel):
     rs = np.random.RandomState(6)
     pcm = [np.clip(rs.randn(n) * 3000, -32768, 32767).astype(np.int16) for n in (4000, 16000, 9999)]
