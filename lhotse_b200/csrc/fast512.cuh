@@ -19,15 +19,14 @@
 
 #include "common.cuh"
 
-#define F512_WARPS 8                        // warps per CTA
-#define F512_HW (2 * F512_WARPS)            // half-warps per CTA
-#define F512_SLOTS 4                        // frames per half-warp per round (mel register blocking)
-#define F512_TILE (F512_HW * F512_SLOTS)    // frames per tile (64)
+// Launch shape is a template parameter set (see Fast512Variant below): WARPS per CTA, SLOTS = frames per half-warp
+// per tile (the mel loop shares each weight across SLOTS frames), TWS = stage-1 twiddles in shared memory instead of
+// 30 registers, MINB = CTAs per SM the register allocator must leave room for.
 #define F512_XROW 18                        // float2 per transpose row (16 + 2 pad: 144 B, LDS.128 conflict-free)
 #define F512_XBUF (16 * F512_XROW)          // float2 per half-warp transpose tile
-#define F512_PBINS 260                      // floats per P row (257 bins; 4*260 = 16 mod 32 keeps the two half-warps of a
-                                            // warp on disjoint banks when they store the same bin of their frames)
-#define F512_PBUF (F512_PBINS * F512_SLOTS) // floats per half-warp P tile, laid out [slot][bin]
+// floats per P row: 257 bins + pad chosen so that SLOTS * PBINS = 16 (mod 32): the two half-warps of a warp then sit on
+// disjoint banks when they store the same bin of their frames
+#define F512_PBINS(SLOTS) ((SLOTS) == 4 ? 260 : 264)
 #ifndef F512_PREFETCH
 #define F512_PREFETCH 1
 #endif
@@ -126,8 +125,9 @@ __device__ __forceinline__ float hw_sum(float v) {  // sum over the 16 lanes of 
   return v;
 }
 
-static inline size_t fast512_smem_bytes(const DevPlan &p, const Fast512Tables &t) {
-  size_t b = (size_t)F512_HW * (F512_XBUF * 8 + F512_PBUF * 4) + F512_PTAIL * 4;
+static inline size_t fast512_smem_bytes(const DevPlan &p, const Fast512Tables &t, int warps, int slots, int tws) {
+  size_t b = (size_t)(2 * warps) * (F512_XBUF * 8 + (size_t)F512_PBINS(slots) * slots * 4) + F512_PTAIL * 4;
+  if (tws) b += 256 * 8;
   b += 16 * 16 * 8;                                   // window pairs
   b += (size_t)t.mel_rounds * 16 * 4 * 2;             // per-round per-lane first bin + output filter
   b += (size_t)t.mel_rounds * 4;                      // per-round trip count
@@ -135,9 +135,13 @@ static inline size_t fast512_smem_bytes(const DevPlan &p, const Fast512Tables &t
   return (b + 15) & ~(size_t)15;
 }
 
-template <int DT, int LCT>
-__global__ void __launch_bounds__(F512_WARPS * 32, 2)
+template <int DT, int LCT, int WARPS, int SLOTS, int TWS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch b) {
+  constexpr int HW = 2 * WARPS;               // half-warps per CTA
+  constexpr int TILE = HW * SLOTS;            // frames per tile
+  constexpr int PBINS = F512_PBINS(SLOTS);
+  constexpr int PBUF = PBINS * SLOTS;         // floats per half-warp P tile, laid out [slot][bin]
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int l = tid & 15;           // lane within the half-warp
@@ -147,26 +151,30 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 
   // ---- shared memory carve-up
   float2 *xall = reinterpret_cast<float2 *>(smem_raw);
-  float *pall = reinterpret_cast<float *>(xall + (size_t)F512_HW * F512_XBUF);
-  float2 *s_win = reinterpret_cast<float2 *>(pall + (size_t)F512_HW * F512_PBUF + F512_PTAIL);
-  int *s_rstart = reinterpret_cast<int *>(s_win + 256);       // [round][lane] first bin of the lane's filter
+  float *pall = reinterpret_cast<float *>(xall + (size_t)HW * F512_XBUF);
+  float2 *s_win = reinterpret_cast<float2 *>(pall + (size_t)HW * PBUF + F512_PTAIL);
+  float2 *s_tw1 = s_win + 256;                                // [k1][lane] stage-1 twiddles (TWS only)
+  int *s_rstart = reinterpret_cast<int *>(s_tw1 + (TWS ? 256 : 0));  // [round][lane] first bin of the lane's filter
   int *s_rlen = s_rstart + ft.mel_rounds * 16;                // [round] trip count (longest filter of the round)
   int *s_rrow = s_rlen + ft.mel_rounds;                       // [round] first weight row
   float *s_mw = reinterpret_cast<float *>(s_rrow + ft.mel_rounds);  // [row][lane] zero-padded weights
   float2 *X = xall + (size_t)hw * F512_XBUF;
-  float *P = pall + (size_t)hw * F512_PBUF;                   // [slot][F512_PBINS]
+  float *P = pall + (size_t)hw * PBUF;                   // [slot][PBINS]
 
   for (int i = tid; i < 256; i += blockDim.x) s_win[i] = __ldg(ft.win2 + i);
+  if (TWS) for (int i = tid; i < 256; i += blockDim.x) s_tw1[i] = __ldg(ft.tw1 + i);
   for (int i = tid; i < ft.mel_rounds * 16; i += blockDim.x) s_rstart[i] = __ldg(ft.rstart + i);
   for (int i = tid; i < ft.mel_rounds; i += blockDim.x) { s_rlen[i] = __ldg(ft.rlen + i); s_rrow[i] = __ldg(ft.rrow + i); }
   for (int i = tid; i < ft.mel_wrows * 16; i += blockDim.x) s_mw[i] = __ldg(ft.wdense + i);
   // P is read past a filter's support with zero weights: it must never hold NaN patterns
-  for (int i = tid; i < F512_HW * F512_PBUF + F512_PTAIL; i += blockDim.x) pall[i] = 0.f;
+  for (int i = tid; i < HW * PBUF + F512_PTAIL; i += blockDim.x) pall[i] = 0.f;
 
   // per-lane constants kept in registers for the whole kernel
-  float2 tw1[16];
+  float2 tw1[TWS ? 1 : 16];
+  if (!TWS) {
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) tw1[k1] = __ldg(ft.tw1 + k1 * 16 + l);
+    for (int k1 = 1; k1 < 16; ++k1) tw1[TWS ? 0 : k1] = __ldg(ft.tw1 + k1 * 16 + l);
+  }
   const float2 w512l = __ldg(ft.w512 + l);
   const int partner = (16 - l) & 15;
   const float inv_L = 1.0f / (float)L;
@@ -175,7 +183,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   for (int64_t tg = blockIdx.x; tg < b.num_tiles; tg += gridDim.x) {
     const int64_t tile = b.tile_base + tg;
     const int cut = __ldg(b.tile_cut + tile) - b.batch_first;  // host-built tile->cut table: one load, no search
-    const int64_t t0 = (tile - __ldg(b.tile_off + cut)) * F512_TILE + (int64_t)hw * F512_SLOTS;
+    const int64_t t0 = (tile - __ldg(b.tile_off + cut)) * TILE + (int64_t)hw * SLOTS;
     const int64_t T = __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut);
     const int64_t rows_here = b.out_mode == B200FEAT_OUT_PADDED ? b.max_frames : T;
     if (!__any_sync(F512_FULL, t0 < rows_here)) continue;  // both halves idle for this tile
@@ -184,10 +192,10 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
     const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED
                              ? (int64_t)(b.batch_first + cut) * b.max_frames + t0
                              : __ldg(b.row_off + cut) + t0;
-    float le[F512_SLOTS];
+    float le[SLOTS];
 
 #pragma unroll 1
-    for (int f = 0; f < F512_SLOTS; ++f) {
+    for (int f = 0; f < SLOTS; ++f) {
       le[f] = 0.f;
       if (!__any_sync(F512_FULL, t0 + f < T)) continue;    // neither half has a frame in this slot
       const int64_t t = min(t0 + f, T - 1);                // an out-of-range half redoes the last frame (not stored)
@@ -283,7 +291,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 #pragma unroll
       for (int k1 = 0; k1 < 16; ++k1) {
         float2 y = v[F512_OUT(k1)];
-        if (k1 > 0) y = f2mul(y, tw1[k1]);
+        if (k1 > 0) y = f2mul(y, TWS ? s_tw1[k1 * 16 + l] : tw1[TWS ? 0 : k1]);
         X[k1 * F512_XROW + l] = y;
       }
       __syncwarp();
@@ -305,7 +313,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       // the mirror's ODD slots (8 complex shuffles instead of 16).  Lane 0 mirrors itself with a one-slot
       // shift (256 - 16*j = 16*(16-j)), so it walks the pairs (0,0) (2,14) (4,12) (6,10) (8,8) (1,15) (3,13) (5,11)
       // here and (7,9) below.  The 1/4 of |X|^2 = |2X|^2/4 is folded into the mel weights / spectrogram epilogue.
-      float *Pf = P + f * F512_PBINS;
+      float *Pf = P + f * PBINS;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         constexpr int kOwn0[8] = {0, 2, 4, 6, 8, 1, 3, 5};
@@ -343,15 +351,15 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
     __syncwarp();
 
     // ---- epilogue over the (up to) 4 frames of this half-warp
-    const int nvalid = (int)max((int64_t)0, min((int64_t)F512_SLOTS, T - t0));
-    const int nrows = (int)max((int64_t)0, min((int64_t)F512_SLOTS, rows_here - t0));
+    const int nvalid = (int)max((int64_t)0, min((int64_t)SLOTS, T - t0));
+    const int nrows = (int)max((int64_t)0, min((int64_t)SLOTS, rows_here - t0));
     float *out = b.out + row0 * p.F;
     if (p.feature == B200FEAT_SPECTROGRAM || p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int f = 0; f < nrows; ++f) {
         float *o = out + (int64_t)f * p.F;
         if (f >= nvalid) { for (int k = l; k < p.F; k += 16) o[k] = b.pad_value; continue; }
         for (int k = l; k < p.K; k += 16) {
-          float x = P[f * F512_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);  // P holds |2X|^2 (or |2X|)
+          float x = P[f * PBINS + k] * (p.use_mag ? 0.5f : 0.25f);  // P holds |2X|^2 (or |2X|)
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
           if (k == 0 && p.use_energy) x = le[f];
           o[k] = x;
@@ -366,30 +374,40 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         const float *Pj = P + s_rstart[j * 16 + l];
         const float *wj = s_mw + s_rrow[j] * 16 + l;
         const int len = s_rlen[j];  // uniform: shorter filters continue on zero weights
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float acc[SLOTS];
+#pragma unroll
+        for (int f = 0; f < SLOTS; ++f) acc[f] = 0.f;
 #pragma unroll 2
         for (int i = 0; i < len; ++i) {
           const float wi = wj[i * 16];
-          a0 = fmaf(Pj[i], wi, a0);
-          a1 = fmaf(Pj[F512_PBINS + i], wi, a1);
-          a2 = fmaf(Pj[2 * F512_PBINS + i], wi, a2);
-          a3 = fmaf(Pj[3 * F512_PBINS + i], wi, a3);
+#pragma unroll
+          for (int f = 0; f < SLOTS; ++f) acc[f] = fmaf(Pj[f * PBINS + i], wi, acc[f]);
         }
         if (m < p.M) {
-          const float r[4] = {__logf(fmaxf(a0, p.mel_floor)), __logf(fmaxf(a1, p.mel_floor)),
-                              __logf(fmaxf(a2, p.mel_floor)), __logf(fmaxf(a3, p.mel_floor))};
-          if (p.feature == B200FEAT_FBANK) {
+          float r[SLOTS];
 #pragma unroll
-            for (int f = 0; f < F512_SLOTS; ++f)
-              if (f < nvalid) out[(int64_t)f * p.F + m + shift] = r[f];
+          for (int f = 0; f < SLOTS; ++f) r[f] = __logf(fmaxf(acc[f], p.mel_floor));
+          if (p.feature == B200FEAT_FBANK) {
+            float *orow = out + m + shift;
+            if (nvalid == SLOTS) {  // the common case: no per-row guards
+#pragma unroll
+              for (int f = 0; f < SLOTS; ++f) orow[(int64_t)f * p.F] = r[f];
+            } else {
+#pragma unroll
+              for (int f = 0; f < SLOTS; ++f)
+                if (f < nvalid) orow[(int64_t)f * p.F] = r[f];
+            }
           } else {
 #pragma unroll
-            for (int f = 0; f < F512_SLOTS; ++f) mlog[f * Mpad + m] = r[f];
+            for (int f = 0; f < SLOTS; ++f) mlog[f * Mpad + m] = r[f];
           }
         }
       }
       if (p.feature == B200FEAT_FBANK) {
-        if (shift && l < nvalid) out[(int64_t)l * p.F] = le[0] * (l == 0) + le[1] * (l == 1) + le[2] * (l == 2) + le[3] * (l == 3);
+        if (shift && l < nvalid) { float v0 = 0.f;
+#pragma unroll
+          for (int f = 0; f < SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
+          out[(int64_t)l * p.F] = v0; }
       } else {
         __syncwarp();
         for (int idx = l; idx < nvalid * p.C; idx += 16) {
@@ -397,7 +415,9 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           float acc = 0.f;
           for (int m = 0; m < p.M; ++m) acc = fmaf(mlog[f * Mpad + m], __ldg(p.dct + m * p.C + c), acc);
           if (p.use_lifter) acc *= __ldg(p.lifter + c);
-          if (p.use_energy && c == 0) acc = le[0] * (f == 0) + le[1] * (f == 1) + le[2] * (f == 2) + le[3] * (f == 3);
+          if (p.use_energy && c == 0) {
+#pragma unroll
+            for (int g = 0; g < SLOTS; ++g) acc = (f == g) ? le[g] : acc; }
           out[(int64_t)f * p.F + c] = acc;
         }
       }
@@ -410,14 +430,33 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 }
 
 // ---------------------------------------------------------------------------------------------- host
+// Launch shapes measured in round 1 on the headline workload (h audio/s, profiles/README.md):
+//   {8 warps, 4 slots, twiddles in registers, 2 CTAs/SM}  3427   <- variant 0, what ships
+//   {8, 4, twiddles in shared memory, 2}                  3272
+//   {10, 2, shared, 2}  (20 warps/SM, 96 registers)       3184
+//   {8, 2, registers, 2}                                  2948   (the 2-frame P tile makes the mel loop 14 % of the loss)
+//   {6, 2, shared, 3}   (18 warps/SM)                     2912
+// Only variants 0 and 2 stay instantiated; B200FEAT_FAST_VARIANT=2 selects the high-occupancy shape for A/B runs.
+struct Fast512Variant { int warps, slots, tws, minb; };
+static const Fast512Variant kFast512Variants[] = {
+    {8, 4, 0, 2},   // 0
+    {8, 4, 0, 2},   // 1 (alias of 0)
+    {10, 2, 1, 2},  // 2
+};
+#define F512_NUM_VARIANTS 3
+#ifndef F512_DEFAULT_VARIANT
+#define F512_DEFAULT_VARIANT 0
+#endif
+
 struct Fast512Host {
   Fast512Tables t;
   size_t smem;
+  int variant;
 };
 
 static inline bool fast512_supported(const DevPlan &p) {
   return p.N == 512 && p.packed && p.L >= 2 && p.L <= 512 && p.C <= 128 &&
-         F512_SLOTS * ((p.M + 3) & ~3) <= 2 * F512_XBUF;  // log-mel staging reuses the transpose tile
+         4 * ((p.M + 3) & ~3) <= 2 * F512_XBUF;  // log-mel staging reuses the transpose tile
 }
 
 template <typename T>
@@ -430,15 +469,47 @@ static int f512_upload(const std::vector<T> &h, std::vector<void *> &allocs, con
   return 0;
 }
 
+// one instantiation per (dtype, compile-time L, variant); `launch` == false only raises the shared-memory limit
+template <int DT, int LCT, int V>
+static int f512_go(bool launch, size_t smem, const DevPlan &p, const Fast512Tables &t, const DevBatch &b, dim3 grid,
+                   cudaStream_t stream) {
+  constexpr int W = V == 2 ? 10 : 8;
+  constexpr int S = V == 2 ? 2 : 4;
+  constexpr int TW = V == 2 ? 1 : 0;
+  constexpr int MB = 2;
+  auto kern = b200feat_fast512_kernel<DT, LCT, W, S, TW, MB>;
+  if (!launch)
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess ? 0 : B200FEAT_ECUDA;
+  kern<<<grid, dim3(W * 32), smem, stream>>>(p, t, b);
+  return 0;
+}
+
 template <int DT, int LCT>
-static int f512_set_attr(size_t smem) {
-  return cudaFuncSetAttribute(b200feat_fast512_kernel<DT, LCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess
-             ? 0 : B200FEAT_ECUDA;
+static int f512_dispatch_variant(int v, bool launch, size_t smem, const DevPlan &p, const Fast512Tables &t, const DevBatch &b,
+                                 dim3 grid, cudaStream_t stream) {
+  if (v == 2) return f512_go<DT, LCT, 2>(launch, smem, p, t, b, grid, stream);
+  return f512_go<DT, LCT, 0>(launch, smem, p, t, b, grid, stream);
+}
+
+static int f512_dispatch(int v, int dt, int L, bool launch, size_t smem, const DevPlan &p, const Fast512Tables &t,
+                         const DevBatch &b, dim3 grid, cudaStream_t stream) {
+  if (L == 400) {
+    if (dt == B200FEAT_I16) return f512_dispatch_variant<B200FEAT_I16, 400>(v, launch, smem, p, t, b, grid, stream);
+    return f512_dispatch_variant<B200FEAT_F32, 400>(v, launch, smem, p, t, b, grid, stream);
+  }
+  if (dt == B200FEAT_I16) return f512_dispatch_variant<B200FEAT_I16, 0>(v, launch, smem, p, t, b, grid, stream);
+  return f512_dispatch_variant<B200FEAT_F32, 0>(v, launch, smem, p, t, b, grid, stream);
 }
 
 static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, std::vector<void *> &allocs,
                                   int *frames_per_tile, const std::vector<float> &window, Fast512Host *out) {
   Fast512Host hst;
+  hst.variant = F512_DEFAULT_VARIANT;
+  if (const char *e = getenv("B200FEAT_FAST_VARIANT")) {
+    const int v = atoi(e);
+    if (v >= 0 && v < F512_NUM_VARIANTS) hst.variant = v;
+  }
+  const Fast512Variant var = kFast512Variants[hst.variant];
   std::vector<float2> win2(256), tw1(256), w512(16);
   for (int n1 = 0; n1 < 16; ++n1)
     for (int l = 0; l < 16; ++l) {
@@ -478,9 +549,8 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
       if (len[l] > mx) mx = len[l];
       rstart[j * 16 + l] = first[l];
     }
-    if (mx > F512_PTAIL) return B200FEAT_EUNSUPPORTED;  // a filter wider than the zeroed slack
-    for (int l = 0; l < 16; ++l)  // zero-weight over-reads must stay inside the frame's own P row
-      if (first[l] + mx > F512_PBINS) return B200FEAT_EUNSUPPORTED;
+    for (int l = 0; l < 16; ++l)  // zero-weight over-reads must stay inside the frame's own (zero-padded) P row
+      if (first[l] + mx > 260) return B200FEAT_EUNSUPPORTED;
     rlen[j] = mx;
     rrow[j] = (int)(wdense.size() / 16);
     for (int i = 0; i < mx; ++i)
@@ -496,28 +566,23 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   if ((rc = f512_upload(wdense, allocs, &hst.t.wdense))) return rc;
   hst.t.mel_rounds = rounds;
   hst.t.mel_wrows = rounds ? (int)(wdense.size() / 16) : 0;
-  hst.smem = fast512_smem_bytes(p, hst.t);
-  if (hst.smem > 113 * 1024) return B200FEAT_EUNSUPPORTED;  // keep 2 CTAs per SM
-  if (f512_set_attr<B200FEAT_F32, 400>(hst.smem) || f512_set_attr<B200FEAT_I16, 400>(hst.smem) ||
-      f512_set_attr<B200FEAT_F32, 0>(hst.smem) || f512_set_attr<B200FEAT_I16, 0>(hst.smem))
-    return B200FEAT_ECUDA;
+  hst.smem = fast512_smem_bytes(p, hst.t, var.warps, var.slots, var.tws);
+  if (hst.smem > (size_t)(227 * 1024 / var.minb) - 1024) return B200FEAT_EUNSUPPORTED;  // keep MINB CTAs per SM
+  DevBatch none{};
+  for (int dt = 0; dt < 2; ++dt)
+    for (int L : {400, 0})
+      if (f512_dispatch(hst.variant, dt, L, false, hst.smem, p, hst.t, none, dim3(1), nullptr)) return B200FEAT_ECUDA;
   *out = hst;
-  *frames_per_tile = F512_TILE;
+  *frames_per_tile = 2 * var.warps * var.slots;
   return 0;
 }
 
 static inline int fast512_launch(const DevPlan &p, const Fast512Host &hst, const DevBatch &b, int dt, int sm_count,
                                  cudaStream_t stream) {
+  const Fast512Variant var = kFast512Variants[hst.variant];
   int64_t blocks = b.num_tiles;
-  const int64_t cap = (int64_t)sm_count * 2;
+  const int64_t cap = (int64_t)sm_count * var.minb;
   if (blocks > cap) blocks = cap;
-  const dim3 grid((unsigned)blocks), block(F512_WARPS * 32);
-  if (p.L == 400) {
-    if (dt == B200FEAT_I16) b200feat_fast512_kernel<B200FEAT_I16, 400><<<grid, block, hst.smem, stream>>>(p, hst.t, b);
-    else b200feat_fast512_kernel<B200FEAT_F32, 400><<<grid, block, hst.smem, stream>>>(p, hst.t, b);
-  } else {
-    if (dt == B200FEAT_I16) b200feat_fast512_kernel<B200FEAT_I16, 0><<<grid, block, hst.smem, stream>>>(p, hst.t, b);
-    else b200feat_fast512_kernel<B200FEAT_F32, 0><<<grid, block, hst.smem, stream>>>(p, hst.t, b);
-  }
+  f512_dispatch(hst.variant, dt, p.L == 400 ? 400 : 0, true, hst.smem, p, hst.t, b, dim3((unsigned)blocks), stream);
   return (int)cudaGetLastError();
 }
