@@ -78,10 +78,13 @@ __device__ __forceinline__ int find_segment(const int64_t *prefix, int B, int64_
   return lo;
 }
 
+// torch.max propagates NaN (fmaxf would drop it): max(x, floor) as the reference computes it
+__device__ __forceinline__ float nanmax(float x, float floor_) { return x < floor_ ? floor_ : x; }
+
 __device__ __forceinline__ float log_energy_value(const DevPlan &p, float e) {
   float le;
-  if (p.energy_style == B200FEAT_ENERGY_KALDI) le = logf(fmaxf(e, 1.1920929e-07f));
+  if (p.energy_style == B200FEAT_ENERGY_KALDI) le = logf(nanmax(e, 1.1920929e-07f));
   else le = logf(e + 1e-15f);
-  if (p.has_energy_floor != 0.0f) le = fmaxf(le, p.energy_floor_log);
+  if (p.has_energy_floor != 0.0f) le = nanmax(le, p.energy_floor_log);
   return le;
 }

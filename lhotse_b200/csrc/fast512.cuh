@@ -386,7 +386,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         if (m < p.M) {
           float r[SLOTS];
 #pragma unroll
-          for (int f = 0; f < SLOTS; ++f) r[f] = __logf(fmaxf(acc[f], p.mel_floor));
+          for (int f = 0; f < SLOTS; ++f) r[f] = __logf(nanmax(acc[f], p.mel_floor));
           if (p.feature == B200FEAT_FBANK) {
             float *orow = out + m + shift;
             if (nvalid == SLOTS) {  // the common case: no per-row guards

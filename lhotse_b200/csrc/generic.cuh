@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         const float *w = p.mel_w + __ldg(p.mel_woff + m);
         float acc = 0.f;
         for (int i = 0; i < len; ++i) acc += raw[st + i] * __ldg(w + i);
-        const float v = logf(fmaxf(acc, p.mel_floor));
+        const float v = logf(nanmax(acc, p.mel_floor));
         if (p.feature == B200FEAT_FBANK) out[m + shift] = v; else mlog[m] = v;
       }
       if (p.feature == B200FEAT_FBANK) {

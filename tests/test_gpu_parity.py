@@ -170,3 +170,47 @@ def test_concurrent_streams():
     torch.cuda.synchronize()
     for a, b in zip(want, got):
         assert torch.equal(a, b)
+
+
+def test_long_recording_and_many_tiny_cuts():
+    """Scale edges: one 30-minute recording (180 000 frames, SURVEY.md §5 'long input') and 5000 ragged
+    0.2-1.2 s cuts in one call.  Interior frames depend only on their own 400 samples, so windows of the long
+    cut are checked against the oracle run on the matching slice."""
+    ext = make("fbank", {})
+    rs = np.random.RandomState(11)
+    n = 30 * 60 * 16000
+    x = (0.1 * rs.randn(n)).astype(np.float32)
+    y = ext.extract(x, 16000)
+    assert y.shape == (180000, 80) and np.isfinite(y).all()
+    cfg = O.OracleConfig()
+    for t0 in (0, 1234, 99990, 179900):
+        t1 = min(t0 + 100, 180000)
+        lo, hi = max(0, (t0 - 12) * 160), min(n, (t1 + 12) * 160)  # slice starts on a hop boundary
+        ref = O.extract(x[lo:hi], cfg)
+        shift = lo // 160  # global index of the slice's frame 0
+        # compare interior frames only (the slice reflects at its own ends)
+        a0 = t0 if lo == 0 else t0 + 2
+        a1 = t1 if hi == n else t1 - 2
+        got = y[a0:a1]
+        want = ref[a0 - shift:a1 - shift]
+        assert got.shape == want.shape and got.shape[0] > 50
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-3)
+    lens = rs.randint(3200, 19200, size=5000)
+    xs = [(0.1 * rs.randn(m)).astype(np.float32) for m in lens]
+    out = ext.extract_batch(xs, 16000)
+    assert len(out) == 5000
+    for i in rs.choice(5000, size=25, replace=False):
+        ref = O.extract(xs[i], cfg)
+        assert out[i].shape == ref.shape
+        np.testing.assert_allclose(out[i], ref, rtol=1e-4, atol=2e-3)
+
+
+def test_nan_inputs_stay_local():
+    """A NaN sample poisons only the frames whose window covers it (as in the reference)."""
+    ext = make("fbank", {})
+    x = (0.1 * np.random.RandomState(3).randn(32000)).astype(np.float32)
+    x[16000] = np.nan
+    y = ext.extract(x, 16000)
+    bad = np.where(~np.isfinite(y).all(axis=1))[0]
+    assert bad.min() >= 98 and bad.max() <= 101 and len(bad) >= 2  # frames whose 400-sample window holds sample 16000
+    assert np.isfinite(y[:98]).all() and np.isfinite(y[102:]).all()
