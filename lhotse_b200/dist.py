@@ -90,3 +90,39 @@ def all_reduce_stats(values: Sequence[float], op: str = "sum") -> List[float]:
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def compute_and_store_features_sharded(cuts, extractor, storage_path, rank: Optional[int] = None,
+                                       world: Optional[int] = None, manifest_name: str = "cuts", **kwargs):
+    """§8e partitioning through lhotse's own batch caller: rank r of W extracts cuts r::W with
+    ``CutSet.compute_and_store_features_batch`` (lhotse/cut/set.py:2197) into ``storage_path/feats-{r}``
+    and writes ``storage_path/{manifest_name}-{r}.jsonl.gz`` — the layout the reference's ``num_jobs`` split
+    produces (set.py:2158-2195), so lhotse's resume logic (``overwrite=False``) and ``combine`` apply per shard.
+    Returns this rank's CutSet with features attached.  Needs lhotse."""
+    from pathlib import Path
+
+    from lhotse import CutSet
+
+    if rank is None or world is None:
+        r, w, _ = env_rank_world()
+        rank = r if rank is None else rank
+        world = w if world is None else world
+    storage_path = Path(storage_path)
+    storage_path.mkdir(parents=True, exist_ok=True)
+    mine = CutSet.from_cuts(shard_iter(cuts, rank, world))
+    return mine.compute_and_store_features_batch(
+        extractor=extractor,
+        storage_path=storage_path / f"feats-{rank}",
+        manifest_path=storage_path / f"{manifest_name}-{rank}.jsonl.gz",
+        **kwargs,
+    )
+
+
+def combine_shards(storage_path, world: int, manifest_name: str = "cuts"):
+    """Rank-0 epilogue: one lazy CutSet over the per-rank manifests, in the original cut order."""
+    from pathlib import Path
+
+    from lhotse import CutSet, load_manifest_lazy
+
+    shards = [list(load_manifest_lazy(Path(storage_path) / f"{manifest_name}-{r}.jsonl.gz")) for r in range(world)]
+    return CutSet.from_cuts(unshard(shards))

@@ -1,0 +1,85 @@
+"""
+"Next" row §8f-1 of the scope contract: the caller right after the hot path.
+
+``FusedOnTheFlyFeatures`` is a drop-in for ``lhotse.dataset.input_strategies.OnTheFlyFeatures``
+(input_strategies.py:351-476) for the B200 extractors: same constructor arguments, same return tuple
+``(feats, feat_lens, [audios, audio_lens], [cuts])``, but the ragged batch is extracted AND collated
+into the padded ``(B, T_max, F)`` tensor (pad value LOG_EPSILON, collation.py:506-533) by ONE kernel
+launch (`B200FEAT_OUT_PADDED`), and the features stay on the GPU for the training step instead of
+bouncing through the per-cut Python copy loop of ``collate_matrices``.
+
+Needs lhotse for audio reading (``read_audio_from_cuts``, collation.py:541); everything numeric
+happens in the extractor.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, List, Optional, Type
+
+import torch
+
+from .plan import LOG_EPSILON
+
+
+class FusedOnTheFlyFeatures:
+    def __init__(
+        self,
+        extractor,
+        wave_transforms: Optional[List[Callable[[torch.Tensor], torch.Tensor]]] = None,
+        num_workers: int = 0,
+        fault_tolerant: bool = False,
+        return_audio: bool = False,
+        executor_type: Type = ThreadPoolExecutor,
+        features_on_device: bool = True,
+    ) -> None:
+        if not hasattr(extractor, "extract_batch_padded"):
+            raise TypeError("FusedOnTheFlyFeatures needs a lhotse_b200 extractor (extract_batch_padded)")
+        self.extractor = extractor
+        self.wave_transforms = list(wave_transforms or [])
+        self.num_workers = num_workers
+        self.fault_tolerant = fault_tolerant
+        self.return_audio = return_audio
+        self.features_on_device = features_on_device
+        self._executor_type = executor_type
+        self._executor = None
+
+    def _get_executor(self):
+        if self.num_workers <= 0:
+            return None
+        if self._executor is None:
+            self._executor = self._executor_type(max_workers=self.num_workers)
+        return self._executor
+
+    def __call__(self, cuts, recording_field: Optional[str] = None):
+        from lhotse.dataset.collation import collate_vectors, read_audio_from_cuts
+
+        audios, cuts = read_audio_from_cuts(
+            cuts, executor=self._get_executor(), suppress_errors=self.fault_tolerant, recording_field=recording_field
+        )
+        for tfnm in self.wave_transforms:
+            for idx in range(len(audios)):
+                audios[idx] = tfnm(audios[idx])
+        sr = cuts[0].sampling_rate
+        assert all(c.sampling_rate == sr for c in cuts), "all cuts of a batch must share one sampling rate"
+        feats, feat_lens = self.extractor.extract_batch_padded(audios, sr, padding_value=LOG_EPSILON)
+        if not self.features_on_device:
+            feats = feats.cpu()
+        out = (feats, feat_lens)
+        if self.return_audio:
+            flat = [a.squeeze(0) if a.dim() > 1 else a for a in audios]
+            audio_lens = torch.tensor([a.shape[0] for a in flat], dtype=torch.int64)
+            out = out + (collate_vectors(flat, padding_value=0), audio_lens)
+        if self.fault_tolerant:
+            out = out + (cuts,)
+        return out
+
+    # lhotse's BatchIO protocol (input_strategies.py:52-110): used by K2SpeechRecognitionDataset for supervisions
+    def supervision_intervals(self, cuts):
+        from lhotse.dataset.input_strategies import OnTheFlyFeatures
+
+        return OnTheFlyFeatures.supervision_intervals(self, cuts)
+
+    def supervision_masks(self, cuts, use_alignment_if_exists: Optional[str] = None):
+        from lhotse.dataset.input_strategies import OnTheFlyFeatures
+
+        return OnTheFlyFeatures.supervision_masks(self, cuts, use_alignment_if_exists)

@@ -1,0 +1,107 @@
+"""§8f 'next' rows, host logic through the REAL lhotse callers (build container only): the fused
+OnTheFlyFeatures replacement and the rank-sharded CutSet extraction.  Numeric engine = oracle-backed fake."""
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+import refshim
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")]
+
+
+@pytest.fixture(scope="module")
+def env(tmp_path_factory):
+    refshim.import_reference()
+    import importlib
+
+    import lhotse_b200.base as lb_base
+    import lhotse_b200.extractors as lb_ex
+
+    importlib.reload(lb_base)
+    importlib.reload(lb_ex)
+    from lhotse import CutSet, MonoCut, Recording, SupervisionSegment
+    from lhotse.audio import AudioSource
+    from lhotse.audio.backend import AudioBackend, LibsndfileCompatibleAudioInfo, set_current_audio_backend
+
+    class WaveBackend(AudioBackend):
+        def read_audio(self, path_or_fd, offset=0.0, duration=None, force_opus_sampling_rate=None):
+            with wave.open(str(path_or_fd)) as w:
+                sr = w.getframerate()
+                w.setpos(int(round(offset * sr)))
+                n = w.getnframes() - w.tell() if duration is None else int(round(duration * sr))
+                pcm = np.frombuffer(w.readframes(n), dtype="<i2")
+            return (pcm.astype(np.float32) / 32768.0)[None, :], sr
+
+        def is_applicable(self, path_or_fd):
+            return True
+
+        def supports_info(self):
+            return True
+
+        def info(self, path_or_fd, force_opus_sampling_rate=None, force_read_audio=False):
+            with wave.open(str(path_or_fd)) as w:
+                return LibsndfileCompatibleAudioInfo(channels=1, frames=w.getnframes(), samplerate=w.getframerate(),
+                                                     duration=w.getnframes() / w.getframerate())
+
+    set_current_audio_backend(WaveBackend())
+    root = tmp_path_factory.mktemp("cuts")
+    rs = np.random.RandomState(0)
+    cuts = []
+    for i, dur in enumerate((1.0, 2.5, 1.7, 3.0, 0.8, 2.0, 1.2)):
+        n = int(dur * 16000)
+        path = root / f"c{i}.wav"
+        with wave.open(str(path), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes(np.clip(rs.randn(n) * 3000, -32768, 32767).astype("<i2").tobytes())
+        rec = Recording(id=f"r{i}", sources=[AudioSource(type="file", channels=[0], source=str(path))],
+                        sampling_rate=16000, num_samples=n, duration=n / 16000)
+        sup = SupervisionSegment(id=f"s{i}", recording_id=f"r{i}", start=0.1, duration=dur - 0.2, text="x")
+        cuts.append(MonoCut(id=f"c{i}", start=0.0, duration=n / 16000, channel=0, recording=rec, supervisions=[sup]))
+    return CutSet.from_cuts(cuts), lb_ex, root
+
+
+def test_fused_on_the_fly_matches_reference_strategy(env):
+    from helpers import attach_oracle_engine
+    from lhotse.dataset.input_strategies import OnTheFlyFeatures
+
+    from lhotse_b200.input_strategies import FusedOnTheFlyFeatures
+
+    cuts, lb_ex, _ = env
+    ext = attach_oracle_engine(lb_ex.B200Fbank())
+    ref_feats, ref_lens = OnTheFlyFeatures(ext)(cuts)
+    fused = FusedOnTheFlyFeatures(ext, return_audio=True)
+    feats, lens, audios, audio_lens = fused(cuts)
+    assert torch.equal(lens, ref_lens) and lens.dtype == torch.int64
+    assert feats.shape == ref_feats.shape and torch.equal(feats, ref_feats)  # same values, same LOG_EPSILON padding
+    assert audios.shape == (7, 48000) and audio_lens.tolist() == [c.num_samples for c in cuts]
+    a = fused.supervision_intervals(cuts)
+    b = OnTheFlyFeatures(ext).supervision_intervals(cuts)
+    assert all(torch.equal(a[k], b[k]) for k in b)
+    # and inside the reference's dataset class (speech_recognition.py:94-116)
+    from lhotse.dataset import K2SpeechRecognitionDataset
+
+    batch = K2SpeechRecognitionDataset(input_strategy=FusedOnTheFlyFeatures(ext))[cuts]
+    assert batch["inputs"].shape[0] == 7 and batch["inputs"].shape[2] == 80
+
+
+def test_rank_sharded_extraction_roundtrip(env):
+    from helpers import attach_oracle_engine
+    from lhotse.features.io import NumpyFilesWriter
+
+    from lhotse_b200 import dist as lbd
+
+    cuts, lb_ex, root = env
+    ext = attach_oracle_engine(lb_ex.B200Fbank())
+    out = root / "sharded"
+    for r in range(2):
+        mine = lbd.compute_and_store_features_sharded(cuts, ext, out, rank=r, world=2, num_workers=0,
+                                                      storage_type=NumpyFilesWriter, batch_duration=4.0)
+        assert [c.id for c in mine] == [c.id for c in cuts][r::2]
+    allc = lbd.combine_shards(out, world=2)
+    assert [c.id for c in allc] == [c.id for c in cuts]
+    for c in allc:
+        assert c.has_features and c.features.type == "b200-fbank"
+        f = c.load_features()
+        assert f.shape == (c.num_frames, 80)
