@@ -44,20 +44,49 @@ struct Fast512Tables {  // device pointers, derived once per handle
   int mel_wrows;        // sum of rlen
 };
 
-__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+// Complex arithmetic on the (re, im) register pair with sm_100 packed-FP32 instructions.  SASS FADD2/FMUL2/FFMA2
+// take operand modifiers that swap the halves and flip one sign (`R.F32x2.LO_HI.NP`), so multiplying by -i / +i is
+// free inside the consuming add, and a complex multiply is FMUL2 + FFMA2 (2 issue slots instead of 4).  The FP32-pipe
+// time is unchanged (a packed op occupies it for two cycles); what halves is the number of issue slots.
+#ifndef F512_PACKED
+#define F512_PACKED 1
+#endif
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+#if F512_PACKED
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+#if F512_PACKED
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+__device__ __forceinline__ float2 f2mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ float2 f2pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
+__device__ __forceinline__ float2 f2conj(float2 a) { return make_float2(a.x, -a.y); }
+#ifndef F512_PACKED_MUL
+#define F512_PACKED_MUL 0
+#endif
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {  // complex product a * b
+#if F512_PACKED_MUL
+  return __ffma2_rn(f2pi(a), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+#else
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+#endif
 }
 
-// forward 4-point DFT, in place, natural order
+// forward 4-point DFT, in place, natural order: 8 complex adds (the two rotations by -/+ i ride on operand modifiers)
 __device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
   const float2 s02 = f2add(a0, a2), d02 = f2sub(a0, a2);
   const float2 s13 = f2add(a1, a3), d13 = f2sub(a1, a3);
   a0 = f2add(s02, s13);
   a2 = f2sub(s02, s13);
-  a1 = make_float2(d02.x + d13.y, d02.y - d13.x);  // d02 - i*d13
-  a3 = make_float2(d02.x - d13.y, d02.y + d13.x);  // d02 + i*d13
+  a1 = f2add(d02, f2mi(d13));  // d02 - i*d13
+  a3 = f2add(d02, f2pi(d13));  // d02 + i*d13
 }
 
 #define F512_C1 0.92387953251128674f  // cos(pi/8)
@@ -68,22 +97,16 @@ __device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 
 __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
-  // v[4c + b] = y[b][c]; twiddle by W16^(b*c)
-  {
-    float2 t;
-    // c = 1: b = 1,2,3 -> W^1, W^2, W^3
-    t = v[5]; v[5] = make_float2(fmaf(t.x, F512_C1, t.y * F512_S1), fmaf(t.y, F512_C1, -t.x * F512_S1));
-    t = v[6]; v[6] = make_float2((t.x + t.y) * F512_R2, (t.y - t.x) * F512_R2);
-    t = v[7]; v[7] = make_float2(fmaf(t.x, F512_S1, t.y * F512_C1), fmaf(t.y, F512_S1, -t.x * F512_C1));
-    // c = 2: b = 1,2,3 -> W^2, W^4, W^6
-    t = v[9]; v[9] = make_float2((t.x + t.y) * F512_R2, (t.y - t.x) * F512_R2);
-    t = v[10]; v[10] = make_float2(t.y, -t.x);
-    t = v[11]; v[11] = make_float2((t.y - t.x) * F512_R2, -(t.x + t.y) * F512_R2);
-    // c = 3: b = 1,2,3 -> W^3, W^6, W^9
-    t = v[13]; v[13] = make_float2(fmaf(t.x, F512_S1, t.y * F512_C1), fmaf(t.y, F512_S1, -t.x * F512_C1));
-    t = v[14]; v[14] = make_float2((t.y - t.x) * F512_R2, -(t.x + t.y) * F512_R2);
-    t = v[15]; v[15] = make_float2(fmaf(-t.x, F512_C1, -t.y * F512_S1), fmaf(t.x, F512_S1, -t.y * F512_C1));
-  }
+  // v[4c + b] = y[b][c]; twiddle by W16^(b*c), W16^m = (cos(pi m/8), -sin(pi m/8))
+  v[5] = f2mul(v[5], make_float2(F512_C1, -F512_S1));    // W^1
+  v[6] = f2mul(v[6], make_float2(F512_R2, -F512_R2));    // W^2
+  v[7] = f2mul(v[7], make_float2(F512_S1, -F512_C1));    // W^3
+  v[9] = f2mul(v[9], make_float2(F512_R2, -F512_R2));    // W^2
+  v[10] = f2mi(v[10]);                                   // W^4 = -i
+  v[11] = f2mul(v[11], make_float2(-F512_R2, -F512_R2)); // W^6
+  v[13] = f2mul(v[13], make_float2(F512_S1, -F512_C1));  // W^3
+  v[14] = f2mul(v[14], make_float2(-F512_R2, -F512_R2)); // W^6
+  v[15] = f2mul(v[15], make_float2(-F512_C1, F512_S1));  // W^9
 #pragma unroll
   for (int c = 0; c < 4; ++c) dft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
@@ -272,14 +295,18 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         if (n1 < NP) {
           const int j0 = 32 * n1 + 2 * l;
           const float2 w = s_win[n1 * 16 + l];  // zero beyond L
-          float da = v[n1].x - mu, dc = v[n1].y - mu, dp = prev[n1] - mu;
-          if (j0 >= L) da = 0.f;
-          if (j0 + 1 >= L) dc = 0.f;
-          if (p.raw_energy) e = fmaf(da, da, fmaf(dc, dc, e));
-          const float ya = fmaf(-p.preemph, dp, da) * w.x;
-          const float yc = fmaf(-p.preemph, da, dc) * w.y;
-          if (!p.raw_energy) e = fmaf(ya, ya, fmaf(yc, yc, e));
-          v[n1] = make_float2(ya, yc);
+          float2 d = f2add(v[n1], make_float2(-mu, -mu));  // (da, dc)
+          const float dp = prev[n1] - mu;
+          if (j0 >= L) d.x = 0.f;
+          if (j0 + 1 >= L) d.y = 0.f;
+          if (p.raw_energy) e = fmaf(d.x, d.x, fmaf(d.y, d.y, e));
+#if F512_PACKED
+          const float2 y = __fmul2_rn(__ffma2_rn(make_float2(dp, d.x), make_float2(-p.preemph, -p.preemph), d), w);
+#else
+          const float2 y = make_float2(fmaf(-p.preemph, dp, d.x) * w.x, fmaf(-p.preemph, d.x, d.y) * w.y);
+#endif
+          if (!p.raw_energy) e = fmaf(y.x, y.x, fmaf(y.y, y.y, e));
+          v[n1] = y;
         } else {
           v[n1] = make_float2(0.f, 0.f);
         }
@@ -322,27 +349,25 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         const float2 zs = v[F512_OUT(15 - 2 * i)], zs0 = v[F512_OUT(kSend0[i])];
         const float2 zk = (i >= 5 && l == 0) ? zo0 : zo;
         const float sx = l == 0 ? zs0.x : zs.x, sy = l == 0 ? zs0.y : zs.y;
-        const float cx = __shfl_sync(F512_FULL, sx, partner, 16);
-        const float cy = __shfl_sync(F512_FULL, sy, partner, 16);
-        const float er = zk.x + cx, ei = zk.y - cy;   // E
-        const float orr = zk.x - cx, oi = zk.y + cy;  // O
+        const float2 cc = f2conj(make_float2(__shfl_sync(F512_FULL, sx, partner, 16), __shfl_sync(F512_FULL, sy, partner, 16)));
+        const float2 E = f2add(zk, cc), O = f2sub(zk, cc);
         float2 wc = w32_const(2 * i);                 // W16^i; lane 0 needs W32^(own slot)
         if (i >= 5) { const float2 w0 = w32_const(kOwn0[i]); wc = l == 0 ? w0 : wc; }
-        const float2 tt = f2mul(f2mul(make_float2(orr, oi), wc), w512l);
-        const float ar = er + tt.y, ai = ei - tt.x;   // 2*X[k]
-        const float br = er - tt.y, bi = ei + tt.x;   // 2*conj(X[256-k])
-        float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+        const float2 mit = f2mi(f2mul(f2mul(O, wc), w512l));  // -i*T
+        const float2 a = f2add(E, mit);               // 2*X[k]
+        const float2 bq = f2sub(E, mit);              // 2*conj(X[256-k])
+        float pa = fmaf(a.x, a.x, a.y * a.y), pb = fmaf(bq.x, bq.x, bq.y * bq.y);
         if (p.use_mag) { pa = sqrtf(pa); pb = sqrtf(pb); }
         const int k = l == 0 ? 16 * kOwn0[i] : l + 32 * i;
         Pf[k] = pa;
         Pf[256 - k] = pb;
       }
       if (l == 0) {  // lane 0's last pair: slots (7, 9) -> bins 112 and 144
-        const float2 zk = v[F512_OUT(7)], zc = v[F512_OUT(9)];
-        const float er = zk.x + zc.x, ei = zk.y - zc.y, orr = zk.x - zc.x, oi = zk.y + zc.y;
-        const float2 tt = f2mul(make_float2(orr, oi), w32_const(7));
-        const float ar = er + tt.y, ai = ei - tt.x, br = er - tt.y, bi = ei + tt.x;
-        float pa = fmaf(ar, ar, ai * ai), pb = fmaf(br, br, bi * bi);
+        const float2 zk = v[F512_OUT(7)], cc = f2conj(v[F512_OUT(9)]);
+        const float2 E = f2add(zk, cc), O = f2sub(zk, cc);
+        const float2 mit = f2mi(f2mul(O, w32_const(7)));
+        const float2 a = f2add(E, mit), bq = f2sub(E, mit);
+        float pa = fmaf(a.x, a.x, a.y * a.y), pb = fmaf(bq.x, bq.x, bq.y * bq.y);
         if (p.use_mag) { pa = sqrtf(pa); pb = sqrtf(pb); }
         Pf[112] = pa;
         Pf[144] = pb;
