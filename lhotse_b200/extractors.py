@@ -81,7 +81,8 @@ class B200FbankConfig(_ConfigMixin):
     norm_filters: bool = False
     torchaudio_compatible_mel_scale: bool = True
     device: str = "cuda"
-    kernel: str = "auto"  # auto | fast | generic
+    kernel: str = "auto"  # auto | fast | fast_x2 | generic
+    compat: str = "lhotse"  # "torchaudio": Kaldi log-energy convention + 2*pi/(L-1) blackman (TorchaudioFbank / KaldifeatFbank)
 
 
 @dataclass
@@ -111,6 +112,7 @@ class B200MfccConfig(_ConfigMixin):
     cepstral_lifter: int = 22
     device: str = "cuda"
     kernel: str = "auto"
+    compat: str = "lhotse"  # "torchaudio": Kaldi log-energy convention, C0 <- energy (TorchaudioMfcc / KaldifeatMfcc)
 
 
 @dataclass
@@ -398,16 +400,45 @@ def install_as_default() -> None:
         _REGISTRY[name] = cls
 
 
-def from_reference_config(cfg: Any, device: str = "cuda"):
-    """Builds the matching B200 extractor from a lhotse FbankConfig/MfccConfig/SpectrogramConfig/
-    LogSpectrogramConfig instance (field names are identical)."""
+def from_reference_config(cfg: Any, device: str = "cuda", sampling_rate: int = 16000):
+    """Builds the matching B200 extractor from one of the reference's config objects:
+      * FbankConfig / MfccConfig / SpectrogramConfig / LogSpectrogramConfig (kaldi/extractors.py) — field names identical;
+      * TorchaudioFbankConfig / TorchaudioMfccConfig (fbank.py:11-39, mfcc.py:9-39) — these carry no sampling rate
+        (torchaudio receives it per call), so pass `sampling_rate`;
+      * KaldifeatFbankConfig / KaldifeatMfccConfig (kaldifeat.py:149-175, :218-246).
+    The torchaudio / kaldifeat families map onto `compat="torchaudio"`."""
     kind = type(cfg).__name__
     table = {"FbankConfig": (B200Fbank, B200FbankConfig), "MfccConfig": (B200Mfcc, B200MfccConfig),
              "SpectrogramConfig": (B200Spectrogram, B200SpectrogramConfig),
              "LogSpectrogramConfig": (B200LogSpectrogram, B200LogSpectrogramConfig)}
-    if kind not in table:
+    if kind in table:
+        cls, ccls = table[kind]
+        d = {k: v for k, v in cfg.to_dict().items() if k in ccls.__dataclass_fields__}
+        d["device"] = device
+        return cls(ccls(**d))
+    is_mfcc = hasattr(cfg, "num_ceps")
+    cls, ccls = (B200Mfcc, B200MfccConfig) if is_mfcc else (B200Fbank, B200FbankConfig)
+    if hasattr(cfg, "preemphasis_coefficient"):  # torchaudio family
+        d = dict(sampling_rate=sampling_rate, frame_length=cfg.frame_length, frame_shift=cfg.frame_shift,
+                 round_to_power_of_two=cfg.round_to_power_of_two, remove_dc_offset=cfg.remove_dc_offset,
+                 preemph_coeff=cfg.preemphasis_coefficient, window_type=cfg.window_type, dither=cfg.dither,
+                 energy_floor=cfg.energy_floor, raw_energy=cfg.raw_energy, use_energy=cfg.use_energy,
+                 low_freq=cfg.low_freq, high_freq=cfg.high_freq, num_filters=cfg.num_mel_bins)
+        if getattr(cfg, "vtln_warp", 1.0) != 1.0:
+            raise ValueError("vtln_warp != 1.0 is not supported")
+    elif hasattr(cfg, "frame_opts"):  # kaldifeat family
+        fo, mo = cfg.frame_opts, cfg.mel_opts
+        if getattr(cfg, "htk_compat", False) or not getattr(cfg, "use_log_fbank", True):
+            raise ValueError("htk_compat=True / use_log_fbank=False are not supported")
+        d = dict(sampling_rate=fo.sampling_rate, frame_length=fo.frame_length, frame_shift=fo.frame_shift,
+                 round_to_power_of_two=fo.round_to_power_of_two, remove_dc_offset=fo.remove_dc_offset,
+                 preemph_coeff=fo.preemph_coeff, window_type=fo.window_type, dither=fo.dither, snip_edges=fo.snip_edges,
+                 energy_floor=cfg.energy_floor, raw_energy=cfg.raw_energy, use_energy=cfg.use_energy,
+                 low_freq=mo.low_freq, high_freq=mo.high_freq, num_filters=mo.num_bins,
+                 use_fft_mag=not getattr(cfg, "use_power", True))
+    else:
         raise ValueError(f"unsupported reference config type {kind}")
-    cls, ccls = table[kind]
-    d = {k: v for k, v in cfg.to_dict().items() if k in ccls.__dataclass_fields__}
-    d["device"] = device
+    if is_mfcc:
+        d.update(num_ceps=cfg.num_ceps, cepstral_lifter=cfg.cepstral_lifter)
+    d.update(device=device, compat="torchaudio")
     return cls(ccls(**d))

@@ -209,7 +209,10 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
         raise ValueError(f"unknown feature kind {feature}")
     frame = _get(cfg, "frame_opts", default=cfg)  # kaldifeat nests the frame options
     melo = _get(cfg, "mel_opts", default=cfg)
-    is_torchaudio = hasattr(cfg, "preemphasis_coefficient")
+    compat = getattr(cfg, "compat", "lhotse")  # our configs carry the family explicitly
+    if compat not in ("lhotse", "torchaudio"):
+        raise ValueError(f"compat must be 'lhotse' or 'torchaudio', got {compat!r}")
+    is_torchaudio = hasattr(cfg, "preemphasis_coefficient") or compat == "torchaudio"
     is_kaldifeat = hasattr(cfg, "frame_opts")
     sr = int(_get(frame, "sampling_rate", default=16000))
     frame_length = float(_get(frame, "frame_length", default=0.025))

@@ -214,3 +214,34 @@ def test_nan_inputs_stay_local():
     bad = np.where(~np.isfinite(y).all(axis=1))[0]
     assert bad.min() >= 98 and bad.max() <= 101 and len(bad) >= 2  # frames whose 400-sample window holds sample 16000
     assert np.isfinite(y[:98]).all() and np.isfinite(y[102:]).all()
+
+
+def _torchaudio_golden():
+    import json
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_torchaudio_v1.npz"))
+    man = json.loads(bytes(g["manifest"]).decode())
+    return [(i, c, g[f"x{i}"], g[f"y{i}"]) for i, c in enumerate(man)]
+
+
+TA_GOLD = _torchaudio_golden()
+
+
+@pytest.mark.parametrize("i,c,x,y", TA_GOLD, ids=[f"{i}-{c['feature']}" for i, c, _, _ in TA_GOLD])
+@pytest.mark.parametrize("kernel", ["generic", "fast"])
+def test_torchaudio_family_golden(kernel, i, c, x, y):
+    """Second oracle: torchaudio.compliance.kaldi outputs (tests/golden/make_golden_torchaudio.py) for the
+    TorchaudioFbank/TorchaudioMfcc config family — Kaldi log-energy convention, energy placement, blackman variant.
+    Gate as in the reference's own comparison test (test/features/test_kaldi_features.py:116-122: rtol 1e-3, atol 1e-4),
+    with the absolute part widened to the fp32 noise floor of log-mel values measured in helpers.py."""
+    from types import SimpleNamespace
+
+    from lhotse_b200 import from_reference_config
+
+    cfg = SimpleNamespace(**c["cfg"])
+    ext = from_reference_config(cfg, sampling_rate=16000)
+    ext.config.kernel = kernel
+    got = ext.extract(x, 16000)
+    assert got.shape == y.shape and ext.engine.kernel == kernel
+    np.testing.assert_allclose(got, y, rtol=1e-3, atol=2e-3 if c["feature"] == "mfcc" else 5e-4)

@@ -105,3 +105,43 @@ def test_tables_equal_live_reference_and_foreign_configs():
     assert (p.L, p.S, p.N, p.num_filters, p.snip_edges) == (400, 160, 512, 80, False)
     p = build_plan("mfcc", KaldifeatMfccConfig())
     assert (p.num_filters, p.num_ceps) == (23, 13) and math.isclose(p.lifter[1], 1 + 11 * math.sin(math.pi / 22), rel_tol=1e-6)
+
+
+def test_compat_flag_and_foreign_config_conversion():
+    from dataclasses import dataclass
+
+    from lhotse_b200 import from_reference_config
+
+    p = build_plan("fbank", B200FbankConfig(compat="torchaudio", window_type="blackman"))
+    q = build_plan("fbank", B200FbankConfig(window_type="blackman"))
+    assert p.energy_style == 1 and q.energy_style == 0
+    assert not np.array_equal(p.window, q.window)  # 2*pi/(L-1) vs 2*pi/L (kaldi.py:104 vs layers.py:931)
+    with pytest.raises(ValueError):
+        build_plan("fbank", B200FbankConfig(compat="htk"))
+
+    @dataclass
+    class TorchaudioMfccConfig:  # stand-in with the reference's field names (lhotse/features/mfcc.py:9-39)
+        dither: float = 0.0
+        window_type: str = "povey"
+        frame_length: float = 0.025
+        frame_shift: float = 0.01
+        remove_dc_offset: bool = True
+        round_to_power_of_two: bool = True
+        energy_floor: float = 1e-10
+        min_duration: float = 0.0
+        preemphasis_coefficient: float = 0.97
+        raw_energy: bool = True
+        low_freq: float = 20.0
+        high_freq: float = -400.0
+        num_mel_bins: int = 23
+        use_energy: bool = False
+        vtln_low: float = 100.0
+        vtln_high: float = -500.0
+        vtln_warp: float = 1.0
+        cepstral_lifter: float = 22.0
+        num_ceps: int = 13
+
+    ext = from_reference_config(TorchaudioMfccConfig(use_energy=True), sampling_rate=8000)
+    assert type(ext).__name__ == "B200Mfcc" and ext.config.compat == "torchaudio" and ext.config.sampling_rate == 8000
+    assert ext.plan.energy_style == 1 and ext.plan.num_filters == 23 and ext.plan.use_energy
+    assert ext.config.preemph_coeff == 0.97 and (ext.plan.L, ext.plan.S, ext.plan.N) == (200, 80, 256)
