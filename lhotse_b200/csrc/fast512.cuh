@@ -14,6 +14,8 @@
 // :32-42 (_rfft/_pow_spectrogram), :565-578 (mel+log), :708-724 (DCT/lifter), with the framing of
 // :727-772 folded into the load addresses.  HBM traffic: 4*S bytes in, 4*F bytes out per frame.
 #pragma once
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -32,17 +34,23 @@
 #endif
 #define F512_PTAIL 64                       // zeroed slack after the last tile (mel reads run past short filters)
 
-struct Fast512Tables {  // device pointers, derived once per handle
-  const float2 *win2;   // [16][16] window pairs (w[32*n1+2l], w[32*n1+2l+1]), zero beyond L
-  const float2 *tw1;    // [16][16] W256^(l*k1) indexed [k1][l]
+struct Fast512Tables {  // derived once per handle
+  // All per-plan constants the kernel keeps in shared memory live in ONE 16-byte-aligned device blob so that a CTA
+  // fetches them with a single bulk asynchronous copy (TMA unit, cp.async.bulk + mbarrier) at start-up:
+  //   [win2: 256 float2 window pairs (w[32*n1+2l], w[32*n1+2l+1]), zero beyond L]
+  //   [tw1 : 256 float2 W256^(l*k1) indexed [k1][l]        (only when the variant keeps them in shared memory)]
+  //   [rstart: rounds*16 int | rlen: rounds int | rrow: rounds int (each padded to 16 B)]
+  //   [wdense: rows*16 float zero-padded mel weights]
+  const void *cblob;
+  int cblob_bytes;
+  int off_tw1, off_rstart, off_rlen, off_rrow, off_mw;  // byte offsets inside the blob
+  const float2 *tw1;    // [16][16] W256^(l*k1) (global copy: loaded into registers by the default variant)
   const float2 *w512;   // [16]     W512^l
-  const int *rstart;    // [rounds][16] first FFT bin of filter m = lane + 16*round (0 if m >= M)
-  const int *rlen;      // [rounds]     trip count of the round = its longest filter
-  const int *rrow;      // [rounds]     first row of the round in wdense
-  const float *wdense;  // [rows][16]   weights, zero-padded to the round's trip count
   int mel_rounds;       // ceil(M / 16)
-  int mel_wrows;        // sum of rlen
+  int mel_wrows;        // sum of the rounds' trip counts
 };
+
+__device__ __forceinline__ unsigned f512_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // Complex arithmetic on the (re, im) register pair with sm_100 packed-FP32 instructions.  SASS FADD2/FMUL2/FFMA2
 // take operand modifiers that swap the halves and flip one sign (`R.F32x2.LO_HI.NP`), so multiplying by -i / +i is
@@ -150,11 +158,9 @@ __device__ __forceinline__ float hw_sum(float v) {  // sum over the 16 lanes of 
 
 static inline size_t fast512_smem_bytes(const DevPlan &p, const Fast512Tables &t, int warps, int slots, int tws) {
   size_t b = (size_t)(2 * warps) * (F512_XBUF * 8 + (size_t)F512_PBINS(slots) * slots * 4) + F512_PTAIL * 4;
-  if (tws) b += 256 * 8;
-  b += 16 * 16 * 8;                                   // window pairs
-  b += (size_t)t.mel_rounds * 16 * 4 * 2;             // per-round per-lane first bin + output filter
-  b += (size_t)t.mel_rounds * 4;                      // per-round trip count
-  b += (size_t)t.mel_wrows * 16 * 4;                  // dense zero-padded weights [row][lane]
+  b += (size_t)t.cblob_bytes;  // constant blob (multiple of 16 B)
+  b += 16;                     // mbarrier
+  (void)p; (void)tws;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -175,20 +181,29 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   // ---- shared memory carve-up
   float2 *xall = reinterpret_cast<float2 *>(smem_raw);
   float *pall = reinterpret_cast<float *>(xall + (size_t)HW * F512_XBUF);
-  float2 *s_win = reinterpret_cast<float2 *>(pall + (size_t)HW * PBUF + F512_PTAIL);
-  float2 *s_tw1 = s_win + 256;                                // [k1][lane] stage-1 twiddles (TWS only)
-  int *s_rstart = reinterpret_cast<int *>(s_tw1 + (TWS ? 256 : 0));  // [round][lane] first bin of the lane's filter
-  int *s_rlen = s_rstart + ft.mel_rounds * 16;                // [round] trip count (longest filter of the round)
-  int *s_rrow = s_rlen + ft.mel_rounds;                       // [round] first weight row
-  float *s_mw = reinterpret_cast<float *>(s_rrow + ft.mel_rounds);  // [row][lane] zero-padded weights
+  unsigned char *s_const = reinterpret_cast<unsigned char *>(pall + (size_t)HW * PBUF + F512_PTAIL);
+  const float2 *s_win = reinterpret_cast<const float2 *>(s_const);
+  const float2 *s_tw1 = reinterpret_cast<const float2 *>(s_const + ft.off_tw1);   // [k1][lane] (TWS only)
+  const int *s_rstart = reinterpret_cast<const int *>(s_const + ft.off_rstart);   // [round][lane] first bin
+  const int *s_rlen = reinterpret_cast<const int *>(s_const + ft.off_rlen);       // [round] trip count
+  const int *s_rrow = reinterpret_cast<const int *>(s_const + ft.off_rrow);       // [round] first weight row
+  const float *s_mw = reinterpret_cast<const float *>(s_const + ft.off_mw);       // [row][lane] zero-padded weights
+  unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_const + ft.cblob_bytes);
   float2 *X = xall + (size_t)hw * F512_XBUF;
-  float *P = pall + (size_t)hw * PBUF;                   // [slot][PBINS]
+  float *P = pall + (size_t)hw * PBUF;                        // [slot][PBINS]
 
-  for (int i = tid; i < 256; i += blockDim.x) s_win[i] = __ldg(ft.win2 + i);
-  if (TWS) for (int i = tid; i < 256; i += blockDim.x) s_tw1[i] = __ldg(ft.tw1 + i);
-  for (int i = tid; i < ft.mel_rounds * 16; i += blockDim.x) s_rstart[i] = __ldg(ft.rstart + i);
-  for (int i = tid; i < ft.mel_rounds; i += blockDim.x) { s_rlen[i] = __ldg(ft.rlen + i); s_rrow[i] = __ldg(ft.rrow + i); }
-  for (int i = tid; i < ft.mel_wrows * 16; i += blockDim.x) s_mw[i] = __ldg(ft.wdense + i);
+  // ---- constant tables: one TMA bulk copy global -> shared, completion signalled on an mbarrier
+  const unsigned bar = f512_smem_u32(s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ft.cblob_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(f512_smem_u32(s_const)), "l"(ft.cblob), "r"(ft.cblob_bytes), "r"(bar) : "memory");
+  }
   // P is read past a filter's support with zero weights: it must never hold NaN patterns
   for (int i = tid; i < HW * PBUF + F512_PTAIL; i += blockDim.x) pall[i] = 0.f;
 
@@ -201,6 +216,12 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   const float2 w512l = __ldg(ft.w512 + l);
   const int partner = (16 - l) & 15;
   const float inv_L = 1.0f / (float)L;
+  {  // every thread observes the completion of the bulk copy (phase 0 of the mbarrier) before touching the tables
+    unsigned done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+  }
   __syncthreads();
 
   for (int64_t tg = blockIdx.x; tg < b.num_tiles; tg += gridDim.x) {
@@ -551,7 +572,6 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
     w512[l] = make_float2((float)cos(a), (float)sin(a));
   }
   int rc;
-  if ((rc = f512_upload(win2, allocs, &hst.t.win2))) return rc;
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
   // mel bank re-packed for the epilogue: round j serves filters 16j..16j+15 (one per lane) with a common
@@ -585,12 +605,27 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
       }
   }
   if (wdense.empty()) wdense.assign(16, 0.f);
-  if ((rc = f512_upload(rstart, allocs, &hst.t.rstart))) return rc;
-  if ((rc = f512_upload(rlen, allocs, &hst.t.rlen))) return rc;
-  if ((rc = f512_upload(rrow, allocs, &hst.t.rrow))) return rc;
-  if ((rc = f512_upload(wdense, allocs, &hst.t.wdense))) return rc;
   hst.t.mel_rounds = rounds;
   hst.t.mel_wrows = rounds ? (int)(wdense.size() / 16) : 0;
+  {  // one 16-byte-aligned blob for the TMA bulk copy
+    std::vector<unsigned char> blob;
+    auto append = [&](const void *src, size_t bytes) -> int {
+      const size_t off = blob.size();
+      blob.resize(off + ((bytes + 15) & ~(size_t)15), 0);
+      memcpy(blob.data() + off, src, bytes);
+      return (int)off;
+    };
+    append(win2.data(), win2.size() * sizeof(float2));
+    hst.t.off_tw1 = var.tws ? append(tw1.data(), tw1.size() * sizeof(float2)) : 0;
+    hst.t.off_rstart = append(rstart.data(), rstart.size() * sizeof(int));
+    hst.t.off_rlen = append(rlen.data(), rlen.size() * sizeof(int));
+    hst.t.off_rrow = append(rrow.data(), rrow.size() * sizeof(int));
+    hst.t.off_mw = append(wdense.data(), wdense.size() * sizeof(float));
+    const unsigned char *d = nullptr;
+    if ((rc = f512_upload(blob, allocs, &d))) return rc;  // cudaMalloc returns >= 256-byte aligned storage
+    hst.t.cblob = d;
+    hst.t.cblob_bytes = (int)blob.size();
+  }
   hst.smem = fast512_smem_bytes(p, hst.t, var.warps, var.slots, var.tws);
   if (hst.smem > (size_t)(227 * 1024 / var.minb) - 1024) return B200FEAT_EUNSUPPORTED;  // keep MINB CTAs per SM
   DevBatch none{};
