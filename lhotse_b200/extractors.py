@@ -15,7 +15,9 @@ Deliberate differences, all documented in DESIGN.md:
   * ``extract_batch`` frames every cut on its own (ragged), so each item equals ``extract`` on that
     item; the reference zero-pads to the longest item and reflects at the *padded* end, which
     perturbs the last 1-2 frames of every shorter item.
-  * ``dither != 0`` is rejected (the reference uses the global torch RNG, layers.py:190-193).
+  * ``dither != 0``: as in the reference (layers.py:190-193) ``dither * N(0,1)`` is added to the *waveform* before
+    framing, drawn from torch's global generator — here the CUDA generator of the extractor's device, so the noise
+    values differ from a CPU run (they also differ between any two reference runs that do not share a seed).
   * ``device`` must be a CUDA device; there is no CPU fallback.
 """
 from __future__ import annotations
@@ -204,10 +206,21 @@ class _B200Extractor(FeatureExtractor):
             "Note you can use CutSet/RecordingSet.resample() to change the audio sampling rate."
         )
 
+    def _dithered(self, buf: torch.Tensor) -> torch.Tensor:
+        """layers.py:190-193: x + dither * randn(x.shape), on the device, from torch's global CUDA generator."""
+        d = float(self.config.dither)
+        if d == 0.0:
+            return buf
+        x = buf.to(torch.float32) * (1.0 / 32768.0) if buf.dtype == torch.int16 else buf
+        return x + d * torch.randn(x.shape, device=x.device, dtype=torch.float32)
+
     def extract(self, samples: ArrayLike, sampling_rate: int) -> ArrayLike:
         self._check_sr(sampling_rate)
         is_numpy = not isinstance(samples, torch.Tensor)
         x = _first_channel_1d(samples)
+        if is_numpy and self.config.dither != 0.0:  # noise is generated on the device: take the tensor route
+            feats = self.extract(torch.from_numpy(np.ascontiguousarray(x)), sampling_rate)
+            return feats.cpu().numpy()
         if is_numpy:
             x = np.ascontiguousarray(x)
             if x.dtype not in (np.float32, np.int16):
@@ -218,7 +231,7 @@ class _B200Extractor(FeatureExtractor):
         if x.dtype not in (torch.float32, torch.int16):
             x = x.to(torch.float32)
         dev = self.engine.device
-        xd = x.to(dev, non_blocking=True)
+        xd = self._dithered(x.to(dev, non_blocking=True))
         feats, _ = self.engine.extract_device(xd, [xd.numel()], offsets=[0])
         return feats.cpu() if self._returns_cpu_tensor else feats
 
@@ -243,7 +256,7 @@ class _B200Extractor(FeatureExtractor):
             buf = samples.contiguous()
             if buf.dtype not in (torch.float32, torch.int16):
                 buf = buf.to(torch.float32)
-            buf = buf.to(eng.device, non_blocking=True).reshape(-1)
+            buf = self._dithered(buf.to(eng.device, non_blocking=True).reshape(-1))
             out, prefix = eng.extract_device(buf, lens, offsets=[i * nmax for i in range(B)])
             result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
             input_is_torch = True
@@ -253,12 +266,12 @@ class _B200Extractor(FeatureExtractor):
             buf = samples.contiguous()
             if buf.dtype not in (torch.float32, torch.int16):
                 buf = buf.to(torch.float32)
-            buf = buf.to(eng.device, non_blocking=True).reshape(-1)
+            buf = self._dithered(buf.to(eng.device, non_blocking=True).reshape(-1))
             lens = [nmax] * B
             out, prefix = eng.extract_device(buf, lens, offsets=[i * nmax for i in range(B)])
             result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
             input_is_torch = True
-        elif isinstance(samples, np.ndarray) and samples.ndim == 2:
+        elif isinstance(samples, np.ndarray) and samples.ndim == 2 and self.config.dither == 0.0:
             # (B, n) array: handed to the C ABI host path as is (rows are back to back)
             B, nmax = samples.shape
             arr = np.ascontiguousarray(samples)
@@ -281,7 +294,13 @@ class _B200Extractor(FeatureExtractor):
                 flat = [(torch.from_numpy(x) if isinstance(x, np.ndarray) else x).squeeze() for x in items]
                 dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
                 buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
-                out, prefix = eng.extract_device(buf, lens, offsets=offs)
+                out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs)
+            elif self.config.dither != 0.0:  # numpy inputs with dither: device route, numpy results
+                flat = [torch.from_numpy(np.ascontiguousarray(np.asarray(x).squeeze())) for x in items]
+                dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
+                buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
+                out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs)
+                out = out.cpu().numpy()
             else:
                 flat = [np.asarray(x).squeeze() for x in items]
                 dt = np.int16 if all(a.dtype == np.int16 for a in flat) else np.float32
@@ -316,7 +335,7 @@ class _B200Extractor(FeatureExtractor):
         eng = self.engine
         flat = [(torch.from_numpy(x) if isinstance(x, np.ndarray) else x).squeeze() for x in samples]
         buf, lens, offs = pack_device(flat, eng.device)
-        out, prefix = eng.extract_device(buf, lens, offsets=offs, out_mode=OUT_PADDED, pad_value=padding_value)
+        out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs, out_mode=OUT_PADDED, pad_value=padding_value)
         feat_lens = torch.from_numpy(np.diff(prefix)).to(torch.int64)
         return out, feat_lens
 

@@ -225,11 +225,8 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
     N = next_power_of_2(L) if rpo2 else L
     window_type = _get(frame, "window_type", default="povey")
     dither = float(_get(frame, "dither", default=0.0))
-    if dither != 0.0:
-        raise ValueError(
-            "dither != 0 is not supported: the reference draws it from the global torch RNG "
-            "(layers.py:190-193), which cannot be reproduced on device; add dither to the waveform upstream."
-        )
+    if dither < 0.0:
+        raise ValueError("dither must be >= 0")
     vtln = float(_get(melo, "vtln_warp", default=1.0))
     if vtln != 1.0:
         raise ValueError("vtln_warp != 1.0 is not supported")

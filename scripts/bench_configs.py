@@ -78,6 +78,21 @@ def main():
         report(name, eng, hours, t_dev, t_host, {"bytes_per_frame": 640 + 4 * eng.feature_dim,
                                                  "algorithmic_GBps": tot.total_rows * (640 + 4 * eng.feature_dim) / t_dev / 1e9})
 
+    # plans outside the N=512 fast path run on the generic kernel (mixed-radix Stockham in shared memory)
+    for name, cfg, sr in (
+        ("fbank80 16k N=400 (round_to_power_of_two=False, radices 4,2,5,5)", lb.B200FbankConfig(round_to_power_of_two=False), 16000),
+        ("fbank40 8k N=256", lb.B200FbankConfig(sampling_rate=8000, num_filters=40), 8000),
+        ("fbank80 24k 50ms N=2048", lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05), 24000),
+        ("fbank80 16k N=512 forced generic", lb.B200FbankConfig(kernel="generic"), 16000),
+    ):
+        eng = Engine(lb.build_plan("fbank", cfg), device=dev, kernel=getattr(cfg, "kernel", "auto"))
+        nn = 10 * sr
+        Bg = 256
+        xg = x[: Bg * nn]
+        lg, og = [nn] * Bg, [i * nn for i in range(Bg)]
+        t_dev, _, tot = time_device(eng, xg, lg, og, reps=5)
+        report(name, eng, Bg * 10 / 3600, t_dev, None, {"frames": int(tot.total_rows)})
+
     # int16 staging: same kernel, half the input bytes over PCIe and HBM
     eng = Engine(lb.build_plan("fbank", lb.B200FbankConfig()), device=dev)
     xi = (x * 32767).clamp(-32768, 32767).to(torch.int16)

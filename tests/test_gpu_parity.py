@@ -245,3 +245,27 @@ def test_torchaudio_family_golden(kernel, i, c, x, y):
     got = ext.extract(x, 16000)
     assert got.shape == y.shape and ext.engine.kernel == kernel
     np.testing.assert_allclose(got, y, rtol=1e-3, atol=2e-3 if c["feature"] == "mfcc" else 5e-4)
+
+
+def test_dither_is_waveform_noise_from_the_device_generator():
+    """layers.py:190-193 semantics: features of (x + dither*randn) with randn from torch's CUDA generator."""
+    x = (0.1 * np.random.RandomState(5).randn(16000)).astype(np.float32)
+    ext = make("fbank", dict(dither=0.01))
+    clean = make("fbank", {})
+    torch.manual_seed(7)
+    a = ext.extract(x, 16000)
+    torch.manual_seed(7)
+    noise = torch.randn(16000, device="cuda")
+    want = clean.extract(torch.from_numpy(x).cuda() + 0.01 * noise, 16000).cpu().numpy()
+    assert np.array_equal(a, want)
+    torch.manual_seed(7)
+    b = ext.extract_batch([x], 16000)[0]
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, clean.extract(x, 16000))
+    # int16 input is scaled before the noise is added, exactly like float input
+    pcm = (x * 32768).astype(np.int16)
+    torch.manual_seed(7)
+    c = ext.extract(pcm, 16000)
+    torch.manual_seed(7)
+    d = ext.extract(pcm.astype(np.float32) / 32768.0, 16000)
+    assert np.array_equal(c, d)

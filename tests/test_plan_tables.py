@@ -64,7 +64,8 @@ def test_plan_dims_and_validation():
     assert build_plan("log-spectrogram", B200LogSpectrogramConfig(round_to_power_of_two=False)).feature_dim == 201
     assert B200Fbank(B200FbankConfig(num_mel_bins=40)).config.num_filters == 40
     with pytest.raises(ValueError):
-        build_plan("fbank", B200FbankConfig(dither=1.0))
+        build_plan("fbank", B200FbankConfig(dither=-1.0))
+    assert build_plan("fbank", B200FbankConfig(dither=1.0)).dither == 1.0
     with pytest.raises(ValueError):
         build_plan("fbank", B200FbankConfig(window_type="kaiser"))
     with pytest.raises(ValueError):
