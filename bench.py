@@ -281,8 +281,7 @@ def run_b200(args):
     # numpy (B, T, 80) — with the samples in pinned host memory: H2D + kernel + D2H inside the timed region
     # (the call lands in the C ABI's b200feat_extract_host, which pipelines the three over 3 streams)
     Be = min(B, args.e2e_batch)
-    ext = lb.B200Fbank(cfg)
-    ext._plan, ext._engine = plan, eng  # same handle / same (broadcast) tables as the device-resident leg
+    ext = lb.B200Fbank(cfg).use_engine(eng)  # same handle / same (broadcast) tables as the device-resident leg
     hx_t = torch.empty((Be, nsamp), dtype=torch.float32, pin_memory=True)
     hx_t.copy_(x[: Be * nsamp].view(Be, nsamp))
     hx = hx_t.numpy()

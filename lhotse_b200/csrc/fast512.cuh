@@ -574,37 +574,13 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   int rc;
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
-  // mel bank re-packed for the epilogue: round j serves filters 16j..16j+15 (one per lane) with a common
-  // trip count; weights beyond a filter's support are zero
-  const int rounds = (p.M + 15) / 16;
-  const float pscale = p.use_mag ? 0.5f : 0.25f;  // the kernel stores |2X|^2 (or |2X|); exact power-of-two rescale
-  std::vector<int> rstart(std::max(rounds, 1) * 16, 0), rlen(std::max(rounds, 1), 0), rrow(std::max(rounds, 1), 0);
-  std::vector<float> wdense;
-  for (int j = 0; j < rounds; ++j) {
-    int first[16], len[16], mx = 0;
-    for (int l = 0; l < 16; ++l) {
-      const int m = l + 16 * j;
-      first[l] = 0; len[l] = 0;
-      if (m < p.M) {
-        int f0 = -1, f1 = -1;
-        for (int k = 0; k < p.K; ++k)
-          if (bank[(size_t)k * p.M + m] != 0.f) { if (f0 < 0) f0 = k; f1 = k; }
-        if (f0 >= 0) { first[l] = f0; len[l] = f1 - f0 + 1; }
-      }
-      if (len[l] > mx) mx = len[l];
-      rstart[j * 16 + l] = first[l];
-    }
-    for (int l = 0; l < 16; ++l)  // zero-weight over-reads must stay inside the frame's own (zero-padded) P row
-      if (first[l] + mx > 260) return B200FEAT_EUNSUPPORTED;
-    rlen[j] = mx;
-    rrow[j] = (int)(wdense.size() / 16);
-    for (int i = 0; i < mx; ++i)
-      for (int l = 0; l < 16; ++l) {
-        const int m = l + 16 * j;
-        wdense.push_back((m < p.M && i < len[l]) ? pscale * bank[(size_t)(first[l] + i) * p.M + m] : 0.f);
-      }
-  }
-  if (wdense.empty()) wdense.assign(16, 0.f);
+  // mel bank re-packed for the epilogue (pack_mel_rounds, common.cuh); the kernel stores |2X|^2 (or |2X|), so the
+  // exact power-of-two factor 1/4 (1/2) rides on the weights
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f);
+  if (mr.max_reach > 260) return B200FEAT_EUNSUPPORTED;  // zero-weight over-reads must stay inside the frame's own P row
+  const int rounds = mr.rounds;
+  const std::vector<int> &rstart = mr.rstart, &rlen = mr.rlen, &rrow = mr.rrow;
+  const std::vector<float> &wdense = mr.wdense;
   hst.t.mel_rounds = rounds;
   hst.t.mel_wrows = rounds ? (int)(wdense.size() / 16) : 0;
   {  // one 16-byte-aligned blob for the TMA bulk copy

@@ -175,6 +175,12 @@ class _B200Extractor(FeatureExtractor):
             self._engine = Engine(self.plan, device=self.config.device, kernel=getattr(self.config, "kernel", "auto"))
         return self._engine
 
+    def use_engine(self, engine: Engine) -> "_B200Extractor":
+        """Adopts an existing handle (e.g. one created after an NCCL broadcast of the constant tables) instead of
+        creating its own on first use."""
+        self._plan, self._engine = engine.plan, engine
+        return self
+
     def __getstate__(self):
         return {"config": self.config}
 
