@@ -81,8 +81,7 @@ def load_library():
                 "lhotse_b200 has no CPU fallback."
             )
         lib = C.CDLL(path)
-        vp, i32, i64, fp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
-        i64p = C.POINTER(C.c_int64)
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
         lib.b200feat_version.restype = C.c_int
         lib.b200feat_global_error.restype = C.c_char_p
         lib.b200feat_create.restype = C.c_int
@@ -155,7 +154,6 @@ class Engine:
         self._h = h
         self.feature_dim = int(self.lib.b200feat_feature_dim(h))
         self.kernel = KERNEL_NAMES[int(self.lib.b200feat_kernel_kind(h))]
-        self._pinned_meta = {}  # per-thread pinned meta staging
 
     def close(self):
         if getattr(self, "_h", None):
