@@ -68,7 +68,7 @@ extern "C" {
 /* kernel selection (b200feat_plan_desc.kernel) */
 #define B200FEAT_KERNEL_AUTO 0
 #define B200FEAT_KERNEL_GENERIC 1 /* any L/S/N, mixed-radix Stockham in shared memory */
-#define B200FEAT_KERNEL_FAST 2    /* register-resident radix-16x16 rFFT, N = 512, one frame per half-warp */
+#define B200FEAT_KERNEL_FAST 2    /* register-resident rFFT: N = 512 (radix 16x16, one frame per half-warp) or N = 256 (16x8, per quarter-warp) */
 #define B200FEAT_KERNEL_FAST_X2 3 /* same algorithm, two frames per half-warp in packed f32x2 (FFMA2/FADD2); experimental */
 
 typedef struct b200feat_plan_desc {

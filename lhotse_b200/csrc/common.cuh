@@ -93,27 +93,27 @@ __device__ __forceinline__ float log_energy_value(const DevPlan &p, float e) {
 }
 
 // ---- host-side helper shared by the N = 512 kernels --------------------------------------------------------------
-// The (K x M) mel bank re-packed for a 16-lane epilogue: round j serves filters 16j..16j+15, one per lane, with a common
+// The (K x M) mel bank re-packed for a `lanes`-wide epilogue (16 or 8): round j serves `lanes` consecutive filters, one per lane, with a common
 // trip count (the round's longest filter); weights beyond a filter's own support are zero, so a shorter filter simply
 // keeps accumulating zeros.  `scale` (an exact power of two) is folded into the weights.
 struct MelRounds {
-  std::vector<int> rstart;    // [rounds][16] first FFT bin of filter m = lane + 16*round (0 if m >= M)
+  std::vector<int> rstart;    // [rounds][lanes] first FFT bin of filter m = lane + lanes*round (0 if m >= M)
   std::vector<int> rlen;      // [rounds]     trip count
   std::vector<int> rrow;      // [rounds]     first row of the round in wdense
-  std::vector<float> wdense;  // [rows][16]
+  std::vector<float> wdense;  // [rows][lanes]
   int rounds = 0, rows = 0;
   int max_reach = 0;          // max over lanes of (first bin + trip count): how far zero-weight over-reads go
 };
 
-static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, int M, float scale) {
+static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, int M, float scale, int lanes = 16) {
   MelRounds r;
-  r.rounds = (M + 15) / 16;
+  r.rounds = (M + lanes - 1) / lanes;
   const int alloc = std::max(r.rounds, 1);
-  r.rstart.assign(alloc * 16, 0); r.rlen.assign(alloc, 0); r.rrow.assign(alloc, 0);
+  r.rstart.assign(alloc * lanes, 0); r.rlen.assign(alloc, 0); r.rrow.assign(alloc, 0);
   for (int j = 0; j < r.rounds; ++j) {
     int first[16], len[16], mx = 0;
-    for (int l = 0; l < 16; ++l) {
-      const int m = l + 16 * j;
+    for (int l = 0; l < lanes; ++l) {
+      const int m = l + lanes * j;
       first[l] = 0; len[l] = 0;
       if (m < M) {
         int f0 = -1, f1 = -1;
@@ -122,18 +122,18 @@ static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, i
         if (f0 >= 0) { first[l] = f0; len[l] = f1 - f0 + 1; }
       }
       mx = std::max(mx, len[l]);
-      r.rstart[j * 16 + l] = first[l];
+      r.rstart[j * lanes + l] = first[l];
     }
-    for (int l = 0; l < 16; ++l) r.max_reach = std::max(r.max_reach, first[l] + mx);
+    for (int l = 0; l < lanes; ++l) r.max_reach = std::max(r.max_reach, first[l] + mx);
     r.rlen[j] = mx;
-    r.rrow[j] = (int)(r.wdense.size() / 16);
+    r.rrow[j] = (int)(r.wdense.size() / lanes);
     for (int i = 0; i < mx; ++i)
-      for (int l = 0; l < 16; ++l) {
-        const int m = l + 16 * j;
+      for (int l = 0; l < lanes; ++l) {
+        const int m = l + lanes * j;
         r.wdense.push_back((m < M && i < len[l]) ? scale * bank[(size_t)(first[l] + i) * M + m] : 0.f);
       }
   }
-  if (r.wdense.empty()) r.wdense.assign(16, 0.f);
-  r.rows = r.rounds ? (int)(r.wdense.size() / 16) : 0;
+  if (r.wdense.empty()) r.wdense.assign(lanes, 0.f);
+  r.rows = r.rounds ? (int)(r.wdense.size() / lanes) : 0;
   return r;
 }

@@ -34,7 +34,9 @@ def make(feature, cfg, kernel="auto"):
 
 def kernels_for(ext):
     """Every kernel that supports the plan is tested (generic always; fast when AUTO picks it)."""
-    return ["generic"] if ext.engine.kernel == "generic" else ["generic", "fast", "fast_x2"]
+    if ext.engine.kernel == "generic":
+        return ["generic"]
+    return ["generic", "fast", "fast_x2"] if ext.plan.N == 512 else ["generic", "fast"]
 
 
 @pytest.mark.parametrize("i,c,x,y", GOLD, ids=IDS)
@@ -269,3 +271,49 @@ def test_dither_is_waveform_noise_from_the_device_generator():
     torch.manual_seed(7)
     d = ext.extract(pcm.astype(np.float32) / 32768.0, 16000)
     assert np.array_equal(c, d)
+
+
+@pytest.mark.parametrize("feature,cfg", [
+    ("fbank", dict(sampling_rate=8000, num_filters=40)),
+    ("fbank", dict(sampling_rate=8000, num_filters=23, use_energy=True)),
+    ("fbank", dict(sampling_rate=8000, num_filters=40, use_fft_mag=True, window_type="hamming", preemph_coeff=0.0)),
+    ("mfcc", dict(sampling_rate=8000)),
+    ("mfcc", dict(sampling_rate=8000, use_energy=True, num_ceps=10)),
+    ("spectrogram", dict(sampling_rate=8000)),
+    ("log-spectrogram", dict(sampling_rate=8000, use_energy=True)),
+    ("fbank", dict(sampling_rate=16000, frame_length=0.016, frame_shift=0.008, num_filters=40)),  # L = N = 256, S = 128
+])
+def test_fast256_kernel_vs_oracle(feature, cfg):
+    """The N = 256 fast kernel (8 kHz geometry and every plan with 128 < L <= 256) against the oracle on ragged lengths
+    that hit the frame-count edges, plus int16 staging and the padded output mode."""
+    sr = cfg["sampling_rate"]
+    ext = make(feature, cfg, kernel="fast")
+    assert ext.engine.kernel == "fast" and ext.plan.N == 256
+    gen = make(feature, cfg, kernel="generic")
+    rs = np.random.RandomState(9)
+    S, L = ext.plan.S, ext.plan.L
+    lens = [L, L + 1, 10 * S - 1, 10 * S + S // 2, 10 * S + S // 2 - 1, 8000, 8003, 20000, 333 * S]
+    xs = [(0.1 * rs.randn(m)).astype(np.float32) for m in lens]
+    xs[3][: len(xs[3]) // 2] *= 1e-4
+    got = ext.extract_batch(xs, sr)
+    ocfg = oracle_cfg(feature, cfg)
+    for x, g in zip(xs, got):
+        ref = O.extract(x, ocfg)
+        truth = O.extract(x, ocfg, dtype=torch.float64)
+        assert g.shape == ref.shape
+        ok, msg = gate(g, ref, truth, feature, cfg.get("use_energy", False), cfg.get("use_fft_mag", False))
+        assert ok, msg
+    for a, b_ in zip(got, gen.extract_batch(xs, sr)):
+        np.testing.assert_allclose(a, b_, rtol=2e-4, atol=5e-4 if feature != "spectrogram" else 1e-3)
+    if feature == "fbank" and not cfg.get("use_energy"):
+        pcm = [np.clip(x * 32768, -32768, 32767).astype(np.int16) for x in xs]
+        i16 = ext.extract_batch(pcm, sr)
+        f32 = ext.extract_batch([q.astype(np.float32) / 32768.0 for q in pcm], sr)
+        for a, b_ in zip(i16, f32):
+            assert np.array_equal(a, b_)
+        feats, flens = ext.extract_batch_padded([torch.from_numpy(x) for x in xs], sr)
+        assert feats.shape[0] == len(xs) and flens.tolist() == [g.shape[0] for g in got]
+        fcpu = feats.cpu().numpy()
+        for i, g in enumerate(got):
+            assert np.array_equal(fcpu[i, : g.shape[0]], g)
+            assert np.all(fcpu[i, g.shape[0]:] == np.float32(LOG_EPSILON))
