@@ -111,7 +111,7 @@ static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, i
   const int alloc = std::max(r.rounds, 1);
   r.rstart.assign(alloc * lanes, 0); r.rlen.assign(alloc, 0); r.rrow.assign(alloc, 0);
   for (int j = 0; j < r.rounds; ++j) {
-    int first[16], len[16], mx = 0;
+    int first[32], len[32], mx = 0;  // lanes <= 32
     for (int l = 0; l < lanes; ++l) {
       const int m = l + lanes * j;
       first[l] = 0; len[l] = 0;

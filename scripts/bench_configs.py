@@ -82,6 +82,9 @@ def main():
     for name, cfg, sr in (
         ("fbank80 16k N=400 (round_to_power_of_two=False, radices 4,2,5,5)", lb.B200FbankConfig(round_to_power_of_two=False), 16000),
         ("fbank40 8k N=256", lb.B200FbankConfig(sampling_rate=8000, num_filters=40), 8000),
+        ("fbank80 24k N=1024 (fast1024)", lb.B200FbankConfig(sampling_rate=24000), 24000),
+        ("fbank80 22.05k N=1024 (fast1024)", lb.B200FbankConfig(sampling_rate=22050), 22050),
+        ("fbank80 24k N=1024 forced generic", lb.B200FbankConfig(sampling_rate=24000, kernel="generic"), 24000),
         ("fbank80 24k 50ms N=2048", lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05), 24000),
         ("fbank80 16k N=512 forced generic", lb.B200FbankConfig(kernel="generic"), 16000),
     ):
