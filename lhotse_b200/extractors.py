@@ -22,6 +22,7 @@ Deliberate differences, all documented in DESIGN.md:
 """
 from __future__ import annotations
 
+import dataclasses
 import warnings
 from dataclasses import asdict, dataclass
 from typing import Any, Dict, List, Optional, Sequence, Union
@@ -159,6 +160,7 @@ class _B200Extractor(FeatureExtractor):
     def __init__(self, config: Optional[Any] = None):
         super().__init__(config=config)
         self._engine: Optional[Engine] = None
+        self._stream_eng: Optional[Engine] = None
         self._plan: Optional[FeaturePlan] = None
         self.plan  # validate the config eagerly (no CUDA needed)
 
@@ -188,6 +190,7 @@ class _B200Extractor(FeatureExtractor):
         self.config = state["config"]
         self._engine = None
         self._plan = None
+        self._stream_eng = None
 
     # -- FeatureExtractor protocol --------------------------------------------------------------
     @property
@@ -199,6 +202,7 @@ class _B200Extractor(FeatureExtractor):
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+        self._stream_eng = None
 
     @property
     def frame_shift(self) -> Seconds:
@@ -330,6 +334,53 @@ class _B200Extractor(FeatureExtractor):
                 return torch.stack(result, dim=0)
             return out.reshape(len(result), result[0].shape[0], result[0].shape[1])
         return result
+
+    # -- streaming ("next") ------------------------------------------------------
+    @property
+    def _stream_engine(self) -> Engine:
+        """Inside a streaming buffer the frames sit at t*S with no padding, i.e. the snip_edges=True framing
+        (layers.py:846-857), so streaming calls run the same kernels through a second handle built from the same
+        config with snip_edges=True."""
+        if getattr(self, "_stream_eng", None) is None:
+            if self.plan.snip_edges:
+                self._stream_eng = self.engine
+            else:
+                plan = build_plan(self.feature_kind, dataclasses.replace(self.config, snip_edges=True))
+                self._stream_eng = Engine(plan, device=self.config.device, kernel=getattr(self.config, "kernel", "auto"))
+        return self._stream_eng
+
+    def online_inference(self, samples: torch.Tensor, context: Optional[torch.Tensor] = None):
+        """Streaming twin of `extract_batch` for a `(B, n)` chunk: `Wav2*.online_inference` (layers.py:199-224,
+        :326-333) over `_get_strided_batch_streaming` (layers.py:775-857).  `context` is the remainder returned by
+        the previous call (None at the start of a recording: the left edge is reflected unless snip_edges).
+        Returns `(features (B, T, F) on the device, remainder (B, r) on the device)`.  A buffer too short for one
+        frame returns T = 0 and the whole buffer as remainder (the reference raises there)."""
+        eng = self._stream_engine
+        x = samples if isinstance(samples, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(samples))
+        assert x.dim() == 2, "online_inference expects a (batch, samples) chunk"
+        x = x.to(eng.device, non_blocking=True)
+        if x.dtype == torch.int16:
+            x = x.to(torch.float32) * (1.0 / 32768.0)
+        x = self._dithered(x.to(torch.float32))  # layers.py:209-212: noise on the new chunk only
+        L, S = self.plan.L, self.plan.S
+        if context is None:
+            if not self.plan.snip_edges:
+                x = torch.cat((torch.flip(x[:, : (L - S) // 2], (1,)), x), dim=1)
+        else:
+            assert context.dim() == 2 and context.size(0) == x.size(0)
+            x = torch.cat((context.to(eng.device, torch.float32), x), dim=1)
+        B, n = x.shape
+        if self.plan.snip_edges:
+            T = 0 if n < L else 1 + (n - L) // S
+        else:
+            T = max(0, (n - (L - S)) // S)
+        remainder = x[:, T * S:]
+        if T == 0:
+            return torch.empty((B, 0, eng.feature_dim), device=eng.device), remainder
+        buf = x.contiguous().reshape(-1)
+        out, prefix = eng.extract_device(buf, [n] * B, offsets=[i * n for i in range(B)])
+        assert int(prefix[1]) == T
+        return out.reshape(B, T, -1), remainder
 
     # -- extras used by the fused-collation ("next", SURVEY.md §8f-1) path -----------------------
     def extract_batch_padded(self, samples: Sequence[torch.Tensor], sampling_rate: int,

@@ -29,7 +29,7 @@ Reference citations (relative to /root/reference):
 from __future__ import annotations
 
 import math
-from dataclasses import astuple, dataclass
+from dataclasses import astuple, dataclass, replace
 from functools import lru_cache
 from typing import Optional, Tuple
 
@@ -308,3 +308,32 @@ def extract(x, cfg: OracleConfig, dtype=torch.float32) -> np.ndarray:
     else:
         raise ValueError(feat)
     return out.numpy()
+
+
+def stream_num_frames(num_samples: int, L: int, S: int, snip_edges: bool) -> int:
+    """Frames that a streaming call emits from a buffer of `num_samples` (= carried remainder + new chunk, plus the
+    reflected left pad on the very first call): layers.py:838-844."""
+    if snip_edges:
+        return 0 if num_samples < L else 1 + (num_samples - L) // S
+    return max(0, (num_samples - (L - S)) // S)
+
+
+def online_inference(chunk, cfg: OracleConfig, context=None, dtype=torch.float32):
+    """Streaming twin of `extract` for one channel: `Wav2*.online_inference` (layers.py:199-224, :326-333) over
+    `_get_strided_batch_streaming` (layers.py:775-857).  `context` is the remainder returned by the previous call
+    (None at the start of a recording).  Returns ((T, F) features, remainder waveform)."""
+    x = torch.as_tensor(np.asarray(chunk)).reshape(-1).to(dtype)
+    L, S, _ = layer_sizes(cfg)
+    if context is None:
+        if not cfg.snip_edges:
+            x = torch.cat((x[: (L - S) // 2].flip(0), x))  # layers.py:826-830
+    else:
+        x = torch.cat((torch.as_tensor(np.asarray(context)).reshape(-1).to(dtype), x))  # layers.py:834
+    T = stream_num_frames(x.numel(), L, S, cfg.snip_edges)
+    remainder = x[T * S:].numpy()
+    if T == 0:
+        F = extract(np.zeros(L, dtype=np.float32), replace(cfg, snip_edges=True)).shape[1]
+        return np.zeros((0, F), dtype=remainder.dtype), remainder
+    # inside the buffer the frames sit at t*S with no padding: exactly the snip_edges=True framing (layers.py:848-857)
+    feats = extract(x[: (T - 1) * S + L], replace(cfg, snip_edges=True), dtype=dtype)
+    return feats, remainder

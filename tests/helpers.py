@@ -23,6 +23,13 @@ def load_golden():
     return [(i, c, g[f"x{i}"], g[f"y{i}"]) for i, c in enumerate(man)]
 
 
+def load_golden_stream():
+    """tests/golden/golden_stream_v1.npz (make_golden_stream.py): reference `online_inference` runs."""
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_stream_v1.npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    return [(i, m, g[f"x{i}"], g[f"y{i}"], g[f"r{i}"]) for i, m in enumerate(meta)]
+
+
 def oracle_cfg(feature, cfg):
     return O.OracleConfig(feature=feature, **cfg)
 
@@ -135,4 +142,9 @@ def attach_oracle_engine(extractor):
     cfg = {k: v for k, v in extractor.config.to_dict().items()
            if k in O.OracleConfig.__dataclass_fields__ and k not in ("feature",)}
     extractor._engine = OracleEngine(extractor.plan, extractor.feature_kind, cfg)
+    import dataclasses
+
+    from lhotse_b200.plan import build_plan
+    snip_plan = build_plan(extractor.feature_kind, dataclasses.replace(extractor.config, snip_edges=True))
+    extractor._stream_eng = OracleEngine(snip_plan, extractor.feature_kind, dict(cfg, snip_edges=True))
     return extractor

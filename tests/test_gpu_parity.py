@@ -366,3 +366,47 @@ def test_fast1024_kernel_vs_oracle(feature, cfg, variant, monkeypatch):
         for i, g in enumerate(got):
             assert np.array_equal(fcpu[i, : g.shape[0]], g)
             assert np.all(fcpu[i, g.shape[0]:] == np.float32(LOG_EPSILON))
+
+
+from helpers import load_golden_stream  # noqa: E402
+
+STREAM = load_golden_stream()
+
+
+@pytest.mark.parametrize("i,m,x,y,r", STREAM, ids=[f"{i}-{m['feature']}" for i, m, _, _, _ in STREAM])
+def test_streaming_online_inference(i, m, x, y, r):
+    """`online_inference` (layers.py:199-224, :326-333, :775-857) on the GPU: per-call frame counts and the carried
+    remainder exactly as the reference's streaming run, values within the gate, and — the reference's own property
+    (test_kaldi_layers.py:199-235) — streaming plus one flipped tail chunk reproduces the offline frames."""
+    ext = make(m["feature"], m["cfg"])
+    sr = m["cfg"].get("sampling_rate", 16000)
+    ocfg = oracle_cfg(m["feature"], m["cfg"])
+    xb = torch.from_numpy(np.stack([x, 0.5 * x, x]))
+    rem, feats, counts = None, [], []
+    for a, b in zip(m["bounds"][:-1], m["bounds"][1:]):
+        f, rem = ext.online_inference(xb[:, a:b], context=rem)
+        assert f.is_cuda and f.dim() == 3 and f.shape[0] == 3
+        feats.append(f)
+        counts.append(f.shape[1])
+    assert counts == m["counts"]
+    assert np.array_equal(rem[0].cpu().numpy(), r)
+    got = torch.cat(feats, dim=1).cpu().numpy()
+    assert np.array_equal(got[0], got[2])  # batch rows are independent
+    assert got[0].shape == y.shape
+    # truth: the float64 oracle on the same streaming schedule
+    rem64, t64 = None, []
+    for a, b in zip(m["bounds"][:-1], m["bounds"][1:]):
+        f64, rem64 = O.online_inference(x[a:b], ocfg, context=rem64, dtype=torch.float64)
+        t64.append(f64)
+    ok, msg = gate(got[0], y, np.concatenate(t64, axis=0), m["feature"], m["cfg"].get("use_energy", False),
+                   m["cfg"].get("use_fft_mag", False))
+    assert ok, msg
+    S = ext.plan.S
+    if not m["cfg"].get("snip_edges", False) and m["n"] % S == 0:
+        tail, _ = ext.online_inference(torch.flip(xb[:, -S:], (1,)), context=rem)
+        online = torch.cat(feats + [tail], dim=1).cpu().numpy()
+        offline = ext.extract_batch(xb, sr)
+        offline = offline.cpu().numpy() if isinstance(offline, torch.Tensor) else np.asarray(offline)
+        assert online.shape == offline.shape
+        # same frames, same arithmetic: the only difference is which load path (interior / edge) fetched the samples
+        assert np.array_equal(online, offline)

@@ -186,3 +186,31 @@ def test_dropin_through_reference_callers(tmp_path):
     # registry round trip through the reference's own from_dict
     again = RefFE.from_dict(ext.to_dict())
     assert type(again).__name__ == "B200Fbank"
+
+
+def test_online_inference_host_logic():
+    """Streaming wrapper (buffer/remainder/frame-count logic of layers.py:775-857) over the fake engine, against the
+    reference's own streaming runs (tests/golden/make_golden_stream.py)."""
+    from helpers import load_golden_stream
+    from lhotse_b200 import B200LogSpectrogramConfig, B200SpectrogramConfig
+    types = {"fbank": (B200Fbank, B200FbankConfig), "mfcc": (B200Mfcc, B200MfccConfig),
+             "spectrogram": (B200Spectrogram, B200SpectrogramConfig),
+             "log-spectrogram": (B200LogSpectrogram, B200LogSpectrogramConfig)}
+    for i, m, x, y, r in load_golden_stream():
+        cls, ccls = types[m["feature"]]
+        ext = attach_oracle_engine(cls(ccls(**m["cfg"])))
+        xb = torch.from_numpy(np.stack([x, -x]))  # batch of two: the negated signal has the same power spectrum
+        rem, feats, counts = None, [], []
+        for a, b in zip(m["bounds"][:-1], m["bounds"][1:]):
+            f, rem = ext.online_inference(xb[:, a:b], context=rem)
+            assert f.dim() == 3 and f.shape[0] == 2
+            feats.append(f)
+            counts.append(f.shape[1])
+        assert counts == m["counts"]
+        assert np.array_equal(rem[0].numpy(), r) and np.array_equal(rem[1].numpy(), -r)
+        got = torch.cat(feats, dim=1).numpy()
+        np.testing.assert_allclose(got[0], y, rtol=1e-4, atol=1e-3 if m["feature"] in ("mfcc", "spectrogram") else 1e-4)
+    # a buffer too short for one frame: nothing emitted, everything carried
+    ext = attach_oracle_engine(B200Fbank())
+    f, rem = ext.online_inference(torch.zeros(1, 100))
+    assert f.shape == (1, 0, 80) and rem.shape == (1, 100 + 100)  # 120-sample reflection is cut to the chunk: 100 + 100

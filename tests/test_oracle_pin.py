@@ -84,3 +84,34 @@ def test_strided_view_equals_closed_form_gather():
         a = O._frames_view(x, L, S, snip)
         b = x[torch.from_numpy(O.frame_index_matrix(n, L, S, snip))]
         assert torch.equal(a, b)
+
+
+from helpers import load_golden_stream  # noqa: E402
+
+STREAM = load_golden_stream()
+
+
+@pytest.mark.parametrize("i,m,x,y,r", STREAM, ids=[f"{i}-{m['feature']}" for i, m, _, _, _ in STREAM])
+def test_oracle_streaming_matches_golden(i, m, x, y, r):
+    """`online_inference` chunk by chunk against the reference's own streaming runs (layers.py:199-224, :326-333,
+    :775-857): frame counts per call and the final remainder exactly, values like the offline goldens."""
+    cfg = oracle_cfg(m["feature"], m["cfg"])
+    rem, feats, counts = None, [], []
+    for a, b in zip(m["bounds"][:-1], m["bounds"][1:]):
+        f, rem = O.online_inference(x[a:b], cfg, context=rem)
+        feats.append(f)
+        counts.append(f.shape[0])
+    assert counts == m["counts"]
+    assert np.array_equal(rem, r)
+    got = np.concatenate(feats, axis=0)
+    assert got.shape == y.shape
+    if not np.array_equal(got, y):
+        np.testing.assert_allclose(got, y, rtol=1e-4, atol=1e-3 if m["feature"] in ("mfcc", "spectrogram") else 1e-4)
+    S = O.layer_sizes(cfg)[1]
+    if not m["cfg"].get("snip_edges", False) and m["n"] % S == 0:
+        # test_kaldi_layers.py:199-235: streaming + one flipped tail chunk reproduces the offline frames
+        tail, rem2 = O.online_inference(x[-S:][::-1].copy(), cfg, context=rem)
+        online = np.concatenate([got, tail], axis=0)
+        offline = O.extract(x, cfg)
+        assert online.shape == offline.shape
+        np.testing.assert_allclose(online, offline, rtol=1e-4, atol=1e-3 if m["feature"] in ("mfcc", "spectrogram") else 1e-4)
