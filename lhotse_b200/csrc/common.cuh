@@ -105,7 +105,10 @@ struct MelRounds {
   int max_reach = 0;          // max over lanes of (first bin + trip count): how far zero-weight over-reads go
 };
 
-static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, int M, float scale, int lanes = 16) {
+static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, int M, float scale, int lanes = 16, int align = 1) {
+  // align > 1: every filter starts on a multiple of `align` bins and trip counts are multiples of `align` (zero weights
+  // fill the gaps), and the weights of `align` consecutive taps of one lane are adjacent: [row / align][lane][align],
+  // so the epilogue can use 64/128-bit shared-memory loads for both operands.
   MelRounds r;
   r.rounds = (M + lanes - 1) / lanes;
   const int alloc = std::max(r.rounds, 1);
@@ -119,19 +122,21 @@ static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, i
         int f0 = -1, f1 = -1;
         for (int k = 0; k < K; ++k)
           if (bank[(size_t)k * M + m] != 0.f) { if (f0 < 0) f0 = k; f1 = k; }
-        if (f0 >= 0) { first[l] = f0; len[l] = f1 - f0 + 1; }
+        if (f0 >= 0) { first[l] = f0 / align * align; len[l] = f1 - first[l] + 1; }
       }
       mx = std::max(mx, len[l]);
       r.rstart[j * lanes + l] = first[l];
     }
+    mx = (mx + align - 1) / align * align;
     for (int l = 0; l < lanes; ++l) r.max_reach = std::max(r.max_reach, first[l] + mx);
     r.rlen[j] = mx;
     r.rrow[j] = (int)(r.wdense.size() / lanes);
-    for (int i = 0; i < mx; ++i)
-      for (int l = 0; l < lanes; ++l) {
-        const int m = l + lanes * j;
-        r.wdense.push_back((m < M && i < len[l]) ? scale * bank[(size_t)(first[l] + i) * M + m] : 0.f);
-      }
+    for (int g = 0; g < mx; g += align)
+      for (int l = 0; l < lanes; ++l)
+        for (int e = 0; e < align; ++e) {
+          const int m = l + lanes * j, i = g + e;
+          r.wdense.push_back((m < M && i < len[l]) ? scale * bank[(size_t)(first[l] + i) * M + m] : 0.f);
+        }
   }
   if (r.wdense.empty()) r.wdense.assign(lanes, 0.f);
   r.rows = r.rounds ? (int)(r.wdense.size() / lanes) : 0;

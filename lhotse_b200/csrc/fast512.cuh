@@ -29,8 +29,16 @@
 // floats per P row: 257 bins + pad chosen so that SLOTS * PBINS = 16 (mod 32): the two half-warps of a warp then sit on
 // disjoint banks when they store the same bin of their frames
 #define F512_PBINS(SLOTS) ((SLOTS) == 4 ? 260 : 264)
+// F512_MEL_ALIGN 2 / 4: filters start on even / 4-aligned bins (zero weights fill in), so the mel loop reads P and the
+// weights with 64 / 128-bit shared-memory loads
+#ifndef F512_MEL_ALIGN
+#define F512_MEL_ALIGN 4
+#endif
+#ifndef F512_MEL_UNROLL
+#define F512_MEL_UNROLL 1
+#endif
 #ifndef F512_PREFETCH
-#define F512_PREFETCH 1
+#define F512_PREFETCH 2
 #endif
 #define F512_PTAIL 64                       // zeroed slack after the last tile (mel reads run past short filters)
 
@@ -247,11 +255,22 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       float2 v[16];
       float prev[NP];
       const bool interior = base >= 0 && base + L <= n && (((xoff + base) & 1) == 0);
-      if (F512_PREFETCH && l < 6) {  // the S new samples of the next frame: pull their lines towards L1 now
+      if (F512_PREFETCH == 1 && l < 6) {  // the S new samples of the next frame: pull their lines towards L1 now
         const int64_t nx = base + L + 32 * l;
         if (nx >= 0 && nx + 32 <= n) {
           const char *pp = reinterpret_cast<const char *>(b.samples) + (xoff + nx) * (DT == B200FEAT_I16 ? 2 : 4);
           asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+        }
+      }
+      if (F512_PREFETCH == 2) {  // one prefetch per 32-byte sector of the next frame's new samples
+        constexpr int PER = DT == B200FEAT_I16 ? 16 : 8;  // samples per sector
+#pragma unroll
+        for (int r = 0; r < (DT == B200FEAT_I16 ? 1 : 2); ++r) {
+          const int64_t nx = base + L + PER * (l + 16 * r);
+          if (nx >= 0 && nx < n && PER * (l + 16 * r) < p.S + PER) {
+            const char *pp = reinterpret_cast<const char *>(b.samples) + (xoff + nx) * (DT == B200FEAT_I16 ? 2 : 4);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
+          }
         }
       }
       if (__all_sync(F512_FULL, interior)) {
@@ -423,12 +442,37 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         float acc[SLOTS];
 #pragma unroll
         for (int f = 0; f < SLOTS; ++f) acc[f] = 0.f;
-#pragma unroll 2
+        constexpr int kMelUnroll = F512_MEL_UNROLL;
+#if F512_MEL_ALIGN == 4
+        const float4 *w4 = reinterpret_cast<const float4 *>(s_mw + s_rrow[j] * 16) + l;
+#pragma unroll kMelUnroll
+        for (int i = 0; i < len; i += 4) {
+          const float4 wi = w4[i * 4];  // [row / 4][lane][4]
+#pragma unroll
+          for (int f = 0; f < SLOTS; ++f) {
+            const float4 pv = *reinterpret_cast<const float4 *>(Pj + f * PBINS + i);
+            acc[f] = fmaf(pv.w, wi.w, fmaf(pv.z, wi.z, fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]))));
+          }
+        }
+#elif F512_MEL_ALIGN == 2
+        const float2 *w2 = reinterpret_cast<const float2 *>(s_mw + s_rrow[j] * 16) + l;
+#pragma unroll kMelUnroll
+        for (int i = 0; i < len; i += 2) {
+          const float2 wi = w2[i * 8];  // [row / 2][lane][2]
+#pragma unroll
+          for (int f = 0; f < SLOTS; ++f) {
+            const float2 pv = *reinterpret_cast<const float2 *>(Pj + f * PBINS + i);
+            acc[f] = fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]));
+          }
+        }
+#else
+#pragma unroll kMelUnroll
         for (int i = 0; i < len; ++i) {
           const float wi = wj[i * 16];
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) acc[f] = fmaf(Pj[f * PBINS + i], wi, acc[f]);
         }
+#endif
         if (m < p.M) {
           float r[SLOTS];
 #pragma unroll
@@ -576,7 +620,7 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
   // mel bank re-packed for the epilogue (pack_mel_rounds, common.cuh); the kernel stores |2X|^2 (or |2X|), so the
   // exact power-of-two factor 1/4 (1/2) rides on the weights
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f);
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, F512_MEL_ALIGN);
   if (mr.max_reach > 260) return B200FEAT_EUNSUPPORTED;  // zero-weight over-reads must stay inside the frame's own P row
   const int rounds = mr.rounds;
   const std::vector<int> &rstart = mr.rstart, &rlen = mr.rlen, &rrow = mr.rrow;

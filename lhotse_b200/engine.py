@@ -65,7 +65,9 @@ EXPORTS = [
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+    """The in-tree library; `B200FEAT_LIBRARY` points a developer run at another build of the same sources
+    (scripts/variant_build.py) — same ABI, same version check."""
+    return os.environ.get("B200FEAT_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 def load_library():
