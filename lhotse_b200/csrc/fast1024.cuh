@@ -275,11 +275,15 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         float acc[SLOTS];
 #pragma unroll
         for (int f = 0; f < SLOTS; ++f) acc[f] = 0.f;
-#pragma unroll 2
-        for (int i = 0; i < len; ++i) {
-          const float wi = wj[i * 32];
+        const float4 *w4 = reinterpret_cast<const float4 *>(wj - lane) + lane;  // [row / 4][lane][4]
+#pragma unroll 1
+        for (int i = 0; i < len; i += 4) {
+          const float4 wi = w4[i * 8];
 #pragma unroll
-          for (int f = 0; f < SLOTS; ++f) acc[f] = fmaf(Pj[f * F1K_PBINS + i], wi, acc[f]);
+          for (int f = 0; f < SLOTS; ++f) {
+            const float4 pv = *reinterpret_cast<const float4 *>(Pj + f * F1K_PBINS + i);
+            acc[f] = fmaf(pv.w, wi.w, fmaf(pv.z, wi.z, fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]))));
+          }
         }
         if (m < p.M) {
           float r[SLOTS];
@@ -394,7 +398,7 @@ static inline int fast1024_prepare(DevPlan &p, const std::vector<float> &bank, s
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
   if ((rc = f512_upload(w1024, allocs, &hst.t.w1024))) return rc;
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 32);
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 32, 4);  // 128-bit mel loads
   if (mr.max_reach > F1K_PBINS) return B200FEAT_EUNSUPPORTED;
   hst.t.mel_rounds = mr.rounds;
   hst.t.mel_wrows = mr.rows;

@@ -297,11 +297,15 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
         float acc[F256_SLOTS];
 #pragma unroll
         for (int f = 0; f < F256_SLOTS; ++f) acc[f] = 0.f;
+        const float2 *w2 = reinterpret_cast<const float2 *>(wj - l) + l;  // [row / 2][lane][2]
 #pragma unroll 2
-        for (int i = 0; i < len; ++i) {
-          const float wi = wj[i * 8];
+        for (int i = 0; i < len; i += 2) {
+          const float2 wi = w2[i * 4];
 #pragma unroll
-          for (int f = 0; f < F256_SLOTS; ++f) acc[f] = fmaf(Pj[f * F256_PBINS + i], wi, acc[f]);
+          for (int f = 0; f < F256_SLOTS; ++f) {
+            const float2 pv = *reinterpret_cast<const float2 *>(Pj + f * F256_PBINS + i);
+            acc[f] = fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]));
+          }
         }
         if (m < p.M) {
           float r[F256_SLOTS];
@@ -394,7 +398,7 @@ static inline int fast256_prepare(DevPlan &p, const std::vector<float> &bank, st
   int rc;
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w256, allocs, &hst.t.w256))) return rc;
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 8);
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 8, 2);  // 64-bit mel loads
   if (mr.max_reach > F256_PBINS) return B200FEAT_EUNSUPPORTED;
   hst.t.mel_rounds = mr.rounds;
   hst.t.mel_wrows = mr.rows;
