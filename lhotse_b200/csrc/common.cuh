@@ -82,7 +82,19 @@ __device__ __forceinline__ int find_segment(const int64_t *prefix, int B, int64_
 }
 
 // torch.max propagates NaN (fmaxf would drop it): max(x, floor) as the reference computes it
-__device__ __forceinline__ float nanmax(float x, float floor_) { return x < floor_ ? floor_ : x; }
+__device__ __forceinline__ float nanmax(float x, float floor_) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(floor_));
+  return r;
+}
+
+// log(x) for x known to be a normal float (the mel floor keeps it >= 1.19e-7): MUFU.LG2 * ln 2, i.e. __logf without its
+// denormal-input fix-up (8 extra instructions per value); NaN and +inf pass through
+__device__ __forceinline__ float fast_log_normal(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.69314718055994530942f;
+}
 
 __device__ __forceinline__ float log_energy_value(const DevPlan &p, float e) {
   float le;

@@ -288,7 +288,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         if (m < p.M) {
           float r[SLOTS];
 #pragma unroll
-          for (int f = 0; f < SLOTS; ++f) r[f] = __logf(nanmax(acc[f], p.mel_floor));
+          for (int f = 0; f < SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[f], p.mel_floor));
           if (p.feature == B200FEAT_FBANK) {
             float *orow = out + m + shift;
 #pragma unroll

@@ -310,7 +310,7 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
         if (m < p.M) {
           float r[F256_SLOTS];
 #pragma unroll
-          for (int f = 0; f < F256_SLOTS; ++f) r[f] = __logf(nanmax(acc[f], p.mel_floor));
+          for (int f = 0; f < F256_SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[f], p.mel_floor));
           if (p.feature == B200FEAT_FBANK) {
             float *orow = out + m + shift;
 #pragma unroll

@@ -29,13 +29,11 @@
 // floats per P row: 257 bins + pad chosen so that SLOTS * PBINS = 16 (mod 32): the two half-warps of a warp then sit on
 // disjoint banks when they store the same bin of their frames
 #define F512_PBINS(SLOTS) ((SLOTS) == 4 ? 260 : 264)
-// F512_MEL_ALIGN 2 / 4: filters start on even / 4-aligned bins (zero weights fill in), so the mel loop reads P and the
-// weights with 64 / 128-bit shared-memory loads
-#ifndef F512_MEL_ALIGN
-#define F512_MEL_ALIGN 4
-#endif
-#ifndef F512_MEL_UNROLL
-#define F512_MEL_UNROLL 1
+// F512_SPLIT_TABLE 1: the real-FFT split reads its twiddle W512^k from a shared-memory table [item][lane] (one 64-bit
+// load) instead of composing it from W16^i (immediates, with a lane-0 select) and W512^l (register): 2 complex
+// multiplies and 6 selects fewer per frame.
+#ifndef F512_SPLIT_TABLE
+#define F512_SPLIT_TABLE 1
 #endif
 #ifndef F512_PREFETCH
 #define F512_PREFETCH 2
@@ -51,7 +49,7 @@ struct Fast512Tables {  // derived once per handle
   //   [wdense: rows*16 float zero-padded mel weights]
   const void *cblob;
   int cblob_bytes;
-  int off_tw1, off_rstart, off_rlen, off_rrow, off_mw;  // byte offsets inside the blob
+  int off_tw1, off_tws, off_rdesc, off_mw;  // byte offsets inside the blob
   const float2 *tw1;    // [16][16] W256^(l*k1) (global copy: loaded into registers by the default variant)
   const float2 *w512;   // [16]     W512^l
   int mel_rounds;       // ceil(M / 16)
@@ -192,10 +190,8 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   unsigned char *s_const = reinterpret_cast<unsigned char *>(pall + (size_t)HW * PBUF + F512_PTAIL);
   const float2 *s_win = reinterpret_cast<const float2 *>(s_const);
   const float2 *s_tw1 = reinterpret_cast<const float2 *>(s_const + ft.off_tw1);   // [k1][lane] (TWS only)
-  const int *s_rstart = reinterpret_cast<const int *>(s_const + ft.off_rstart);   // [round][lane] first bin
-  const int *s_rlen = reinterpret_cast<const int *>(s_const + ft.off_rlen);       // [round] trip count
-  const int *s_rrow = reinterpret_cast<const int *>(s_const + ft.off_rrow);       // [round] first weight row
-  const float *s_mw = reinterpret_cast<const float *>(s_const + ft.off_mw);       // [row][lane] zero-padded weights
+  const int4 *s_rdesc = reinterpret_cast<const int4 *>(s_const + ft.off_rdesc);   // [round][lane] mel round descriptors
+  const float4 *s_mw4 = reinterpret_cast<const float4 *>(s_const + ft.off_mw);    // [row / 4][lane][4] zero-padded weights
   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_const + ft.cblob_bytes);
   float2 *X = xall + (size_t)hw * F512_XBUF;
   float *P = pall + (size_t)hw * PBUF;                        // [slot][PBINS]
@@ -221,7 +217,11 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) tw1[TWS ? 0 : k1] = __ldg(ft.tw1 + k1 * 16 + l);
   }
+#if F512_SPLIT_TABLE
+  const float2 *s_tws = reinterpret_cast<const float2 *>(s_const + ft.off_tws) + l;  // [item][lane] W512^k of the split
+#else
   const float2 w512l = __ldg(ft.w512 + l);
+#endif
   const int partner = (16 - l) & 15;
   const float inv_L = 1.0f / (float)L;
   {  // every thread observes the completion of the bulk copy (phase 0 of the mbarrier) before touching the tables
@@ -244,38 +244,43 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
     const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED
                              ? (int64_t)(b.batch_first + cut) * b.max_frames + t0
                              : __ldg(b.row_off + cut) + t0;
+    // Everything per frame below is 32-bit arithmetic relative to the half-warp's first frame `tb`:
+    //   frame t = tb + fl, fl = min(f, tmax)  (an out-of-range half redoes the cut's last frame and does not store it)
+    //   first sample of the frame = base0 + rel, rel = fl * S
+    const int64_t tb = min(t0, T - 1);
+    const int tmax = (int)min(T - 1 - tb, (int64_t)(SLOTS - 1));
+    const int nv = (int)max((int64_t)0, min((int64_t)SLOTS, T - t0));  // frames of this half that exist
+    const int64_t base0 = tb * p.S - (p.snip_edges ? 0 : p.pad_left);
+    constexpr int64_t kClamp = 1 << 30;
+    const int rel_lo = (int)max(-kClamp, min(kClamp, -base0));           // frame starts inside the cut:  rel >= rel_lo
+    const int rel_hi = (int)max(-kClamp, min(kClamp, n - L - base0));    // frame ends inside the cut:    rel <= rel_hi
+    const int rel_end = (int)max(-kClamp, min(kClamp, n - 1 - base0));   // last sample of the cut, relative
+    const int par0 = (int)((xoff + base0) & 1);                          // 8-byte alignment of the 64-bit loads
+    const char *cut0 = reinterpret_cast<const char *>(b.samples) + (xoff + base0) * (DT == B200FEAT_I16 ? 2 : 4);
     float le[SLOTS];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) le[k] = 0.f;
 
 #pragma unroll 1
     for (int f = 0; f < SLOTS; ++f) {
-      le[f] = 0.f;
-      if (!__any_sync(F512_FULL, t0 + f < T)) continue;    // neither half has a frame in this slot
-      const int64_t t = min(t0 + f, T - 1);                // an out-of-range half redoes the last frame (not stored)
-      const int64_t base = t * p.S - (p.snip_edges ? 0 : p.pad_left);
+      if (!__any_sync(F512_FULL, f < nv)) continue;        // neither half has a frame in this slot
+      const int rel = min(f, tmax) * p.S;
+      const int64_t base = base0 + rel;                    // only the (rare) edge path uses the 64-bit form
       float2 v[16];
       float prev[NP];
-      const bool interior = base >= 0 && base + L <= n && (((xoff + base) & 1) == 0);
-      if (F512_PREFETCH == 1 && l < 6) {  // the S new samples of the next frame: pull their lines towards L1 now
-        const int64_t nx = base + L + 32 * l;
-        if (nx >= 0 && nx + 32 <= n) {
-          const char *pp = reinterpret_cast<const char *>(b.samples) + (xoff + nx) * (DT == B200FEAT_I16 ? 2 : 4);
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
-        }
-      }
-      if (F512_PREFETCH == 2) {  // one prefetch per 32-byte sector of the next frame's new samples
+      const bool interior = rel >= rel_lo && rel <= rel_hi && (((par0 + rel) & 1) == 0);
+      if (F512_PREFETCH == 2) {  // one L1 prefetch per 32-byte sector of the next frame's new samples
         constexpr int PER = DT == B200FEAT_I16 ? 16 : 8;  // samples per sector
 #pragma unroll
         for (int r = 0; r < (DT == B200FEAT_I16 ? 1 : 2); ++r) {
-          const int64_t nx = base + L + PER * (l + 16 * r);
-          if (nx >= 0 && nx < n && PER * (l + 16 * r) < p.S + PER) {
-            const char *pp = reinterpret_cast<const char *>(b.samples) + (xoff + nx) * (DT == B200FEAT_I16 ? 2 : 4);
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pp));
-          }
+          const int q = rel + L + PER * (l + 16 * r);
+          if (q >= rel_lo && q <= rel_end && PER * (l + 16 * r) < p.S + PER)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(cut0 + (int64_t)q * (DT == B200FEAT_I16 ? 2 : 4)));
         }
       }
       if (__all_sync(F512_FULL, interior)) {
         if (DT == B200FEAT_I16) {
-          const int16_t *xp = reinterpret_cast<const int16_t *>(b.samples) + (xoff + base + 2 * l);
+          const int16_t *xp = reinterpret_cast<const int16_t *>(cut0) + (rel + 2 * l);
 #pragma unroll
           for (int n1 = 0; n1 < NP; ++n1) {
             const int j0 = 32 * n1 + 2 * l;
@@ -290,7 +295,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
             if (j0 < L) prev[n1] = (float)__ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0)) * (1.0f / 32768.0f);
           }
         } else {
-          const float *xp = reinterpret_cast<const float *>(b.samples) + (xoff + base + 2 * l);
+          const float *xp = reinterpret_cast<const float *>(cut0) + (rel + 2 * l);
 #pragma unroll
           for (int n1 = 0; n1 < NP; ++n1) {
             const int j0 = 32 * n1 + 2 * l;
@@ -351,7 +356,11 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           v[n1] = make_float2(0.f, 0.f);
         }
       }
-      if (p.use_energy) le[f] = log_energy_value(p, hw_sum(e));
+      if (p.use_energy) {  // le[] stays in registers: no dynamic indexing
+        const float lev = log_energy_value(p, hw_sum(e));
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) le[k] = (f == k) ? lev : le[k];
+      }
 
       // ---- stage 1: radix-16 over n1, twiddle, transpose
       dft16(v);
@@ -391,9 +400,13 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         const float sx = l == 0 ? zs0.x : zs.x, sy = l == 0 ? zs0.y : zs.y;
         const float2 cc = f2conj(make_float2(__shfl_sync(F512_FULL, sx, partner, 16), __shfl_sync(F512_FULL, sy, partner, 16)));
         const float2 E = f2add(zk, cc), O = f2sub(zk, cc);
+#if F512_SPLIT_TABLE
+        const float2 mit = f2mi(f2mul(O, s_tws[i * 16]));     // -i*T, T = W512^k * O from the [item][lane] table
+#else
         float2 wc = w32_const(2 * i);                 // W16^i; lane 0 needs W32^(own slot)
         if (i >= 5) { const float2 w0 = w32_const(kOwn0[i]); wc = l == 0 ? w0 : wc; }
         const float2 mit = f2mi(f2mul(f2mul(O, wc), w512l));  // -i*T
+#endif
         const float2 a = f2add(E, mit);               // 2*X[k]
         const float2 bq = f2sub(E, mit);              // 2*conj(X[256-k])
         float pa = fmaf(a.x, a.x, a.y * a.y), pb = fmaf(bq.x, bq.x, bq.y * bq.y);
@@ -416,7 +429,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
     __syncwarp();
 
     // ---- epilogue over the (up to) 4 frames of this half-warp
-    const int nvalid = (int)max((int64_t)0, min((int64_t)SLOTS, T - t0));
+    const int nvalid = nv;
     const int nrows = (int)max((int64_t)0, min((int64_t)SLOTS, rows_here - t0));
     float *out = b.out + row0 * p.F;
     if (p.feature == B200FEAT_SPECTROGRAM || p.feature == B200FEAT_LOG_SPECTROGRAM) {
@@ -426,7 +439,10 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         for (int k = l; k < p.K; k += 16) {
           float x = P[f * PBINS + k] * (p.use_mag ? 0.5f : 0.25f);  // P holds |2X|^2 (or |2X|)
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
-          if (k == 0 && p.use_energy) x = le[f];
+          if (k == 0 && p.use_energy) {
+#pragma unroll
+            for (int g = 0; g < SLOTS; ++g) x = (f == g) ? le[g] : x;
+          }
           o[k] = x;
         }
       }
@@ -436,47 +452,25 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       float *mlog = reinterpret_cast<float *>(X);  // the transpose tile is idle during the epilogue
       for (int j = 0; j < ft.mel_rounds; ++j) {
         const int m = l + 16 * j;
-        const float *Pj = P + s_rstart[j * 16 + l];
-        const float *wj = s_mw + s_rrow[j] * 16 + l;
-        const int len = s_rlen[j];  // uniform: shorter filters continue on zero weights
+        const int4 rd = s_rdesc[j * 16 + l];  // {first bin (multiple of 4), trip count (uniform), weight index, -}
+        const float4 *pp = reinterpret_cast<const float4 *>(P + rd.x);
+        const float4 *wp = s_mw4 + rd.z;      // weights [row / 4][lane][4]: one 128-bit load feeds 4 taps x SLOTS frames
         float acc[SLOTS];
 #pragma unroll
         for (int f = 0; f < SLOTS; ++f) acc[f] = 0.f;
-        constexpr int kMelUnroll = F512_MEL_UNROLL;
-#if F512_MEL_ALIGN == 4
-        const float4 *w4 = reinterpret_cast<const float4 *>(s_mw + s_rrow[j] * 16) + l;
-#pragma unroll kMelUnroll
-        for (int i = 0; i < len; i += 4) {
-          const float4 wi = w4[i * 4];  // [row / 4][lane][4]
+#pragma unroll 1
+        for (int i = rd.y; i > 0; i -= 4, ++pp, wp += 16) {
+          const float4 wi = *wp;
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) {
-            const float4 pv = *reinterpret_cast<const float4 *>(Pj + f * PBINS + i);
+            const float4 pv = pp[f * (PBINS / 4)];
             acc[f] = fmaf(pv.w, wi.w, fmaf(pv.z, wi.z, fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]))));
           }
         }
-#elif F512_MEL_ALIGN == 2
-        const float2 *w2 = reinterpret_cast<const float2 *>(s_mw + s_rrow[j] * 16) + l;
-#pragma unroll kMelUnroll
-        for (int i = 0; i < len; i += 2) {
-          const float2 wi = w2[i * 8];  // [row / 2][lane][2]
-#pragma unroll
-          for (int f = 0; f < SLOTS; ++f) {
-            const float2 pv = *reinterpret_cast<const float2 *>(Pj + f * PBINS + i);
-            acc[f] = fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]));
-          }
-        }
-#else
-#pragma unroll kMelUnroll
-        for (int i = 0; i < len; ++i) {
-          const float wi = wj[i * 16];
-#pragma unroll
-          for (int f = 0; f < SLOTS; ++f) acc[f] = fmaf(Pj[f * PBINS + i], wi, acc[f]);
-        }
-#endif
         if (m < p.M) {
           float r[SLOTS];
 #pragma unroll
-          for (int f = 0; f < SLOTS; ++f) r[f] = __logf(nanmax(acc[f], p.mel_floor));
+          for (int f = 0; f < SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[f], p.mel_floor));
           if (p.feature == B200FEAT_FBANK) {
             float *orow = out + m + shift;
             if (nvalid == SLOTS) {  // the common case: no per-row guards
@@ -620,7 +614,7 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
   // mel bank re-packed for the epilogue (pack_mel_rounds, common.cuh); the kernel stores |2X|^2 (or |2X|), so the
   // exact power-of-two factor 1/4 (1/2) rides on the weights
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, F512_MEL_ALIGN);
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, 4);  // 4-aligned filter starts: 128-bit mel loads
   if (mr.max_reach > 260) return B200FEAT_EUNSUPPORTED;  // zero-weight over-reads must stay inside the frame's own P row
   const int rounds = mr.rounds;
   const std::vector<int> &rstart = mr.rstart, &rlen = mr.rlen, &rrow = mr.rrow;
@@ -637,9 +631,24 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
     };
     append(win2.data(), win2.size() * sizeof(float2));
     hst.t.off_tw1 = var.tws ? append(tw1.data(), tw1.size() * sizeof(float2)) : 0;
-    hst.t.off_rstart = append(rstart.data(), rstart.size() * sizeof(int));
-    hst.t.off_rlen = append(rlen.data(), rlen.size() * sizeof(int));
-    hst.t.off_rrow = append(rrow.data(), rrow.size() * sizeof(int));
+    {  // split twiddles W512^k for the bin each (item, lane) handles: k = l + 32 i, lane 0: k = 16 * (its own slot)
+      static const int kOwn0[8] = {0, 2, 4, 6, 8, 1, 3, 5};
+      std::vector<float2> tws(8 * 16);
+      for (int i = 0; i < 8; ++i)
+        for (int l = 0; l < 16; ++l) {
+          const int k = l == 0 ? 16 * kOwn0[i] : l + 32 * i;
+          const double a = -2.0 * M_PI * (double)k / 512.0;
+          tws[i * 16 + l] = make_float2((float)cos(a), (float)sin(a));
+        }
+      hst.t.off_tws = append(tws.data(), tws.size() * sizeof(float2));
+    }
+    std::vector<int> rdesc((size_t)std::max(rounds, 1) * 16 * 4, 0);  // per (round, lane): {first bin, trips, weight idx, 0}
+    for (int j = 0; j < rounds; ++j)
+      for (int l = 0; l < 16; ++l) {
+        int *d = &rdesc[((size_t)j * 16 + l) * 4];
+        d[0] = rstart[j * 16 + l]; d[1] = rlen[j]; d[2] = rrow[j] * 4 + l;  // float4 index of the lane's first weights
+      }
+    hst.t.off_rdesc = append(rdesc.data(), rdesc.size() * sizeof(int));
     hst.t.off_mw = append(wdense.data(), wdense.size() * sizeof(float));
     const unsigned char *d = nullptr;
     if ((rc = f512_upload(blob, allocs, &d))) return rc;  // cudaMalloc returns >= 256-byte aligned storage

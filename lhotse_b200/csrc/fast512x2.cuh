@@ -362,7 +362,7 @@ b200feat_fast512x2_kernel(const DevPlan p, const FastX2Tables ft, const DevBatch
 #pragma unroll 4
           for (int i = 0; i < len; ++i) acc = pfma(Pj[i], bc(wj[i * 16]), acc);
           if (m < p.M) {
-            const float ra = __logf(nanmax(acc.x, p.mel_floor)), rb = __logf(nanmax(acc.y, p.mel_floor));
+            const float ra = fast_log_normal(nanmax(acc.x, p.mel_floor)), rb = fast_log_normal(nanmax(acc.y, p.mel_floor));
             if (p.feature == B200FEAT_FBANK) {
               if (vA) outA[m + shift] = ra;
               if (vB) outB[m + shift] = rb;
