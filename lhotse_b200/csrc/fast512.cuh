@@ -29,11 +29,9 @@
 // floats per P row: 257 bins + pad chosen so that SLOTS * PBINS = 16 (mod 32): the two half-warps of a warp then sit on
 // disjoint banks when they store the same bin of their frames
 #define F512_PBINS(SLOTS) ((SLOTS) == 4 ? 260 : 264)
-// F512_SPLIT_TABLE 1: the real-FFT split reads its twiddle W512^k from a shared-memory table [item][lane] (one 64-bit
-// load) instead of composing it from W16^i (immediates, with a lane-0 select) and W512^l (register): 2 complex
-// multiplies and 6 selects fewer per frame.
-#ifndef F512_SPLIT_TABLE
-#define F512_SPLIT_TABLE 1
+// F512_PREV_SHFL 1: the pre-emphasis neighbour x[j-1] comes from the adjacent lane by shuffle instead of a second load
+#ifndef F512_PREV_SHFL
+#define F512_PREV_SHFL 1
 #endif
 #ifndef F512_PREFETCH
 #define F512_PREFETCH 2
@@ -49,7 +47,7 @@ struct Fast512Tables {  // derived once per handle
   //   [wdense: rows*16 float zero-padded mel weights]
   const void *cblob;
   int cblob_bytes;
-  int off_tw1, off_tws, off_rdesc, off_mw;  // byte offsets inside the blob
+  int off_tw1, off_rdesc, off_mw;  // byte offsets inside the blob
   const float2 *tw1;    // [16][16] W256^(l*k1) (global copy: loaded into registers by the default variant)
   const float2 *w512;   // [16]     W512^l
   int mel_rounds;       // ceil(M / 16)
@@ -217,11 +215,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) tw1[TWS ? 0 : k1] = __ldg(ft.tw1 + k1 * 16 + l);
   }
-#if F512_SPLIT_TABLE
-  const float2 *s_tws = reinterpret_cast<const float2 *>(s_const + ft.off_tws) + l;  // [item][lane] W512^k of the split
-#else
   const float2 w512l = __ldg(ft.w512 + l);
-#endif
   const int partner = (16 - l) & 15;
   const float inv_L = 1.0f / (float)L;
   {  // every thread observes the completion of the bulk copy (phase 0 of the mbarrier) before touching the tables
@@ -292,7 +286,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
             } else if (j0 < L) {
               v[n1].x = (float)__ldg(xp + 32 * n1) * (1.0f / 32768.0f);
             }
-            if (j0 < L) prev[n1] = (float)__ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0)) * (1.0f / 32768.0f);
+            if (!F512_PREV_SHFL && j0 < L) prev[n1] = (float)__ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0)) * (1.0f / 32768.0f);
           }
         } else {
           const float *xp = reinterpret_cast<const float *>(cut0) + (rel + 2 * l);
@@ -303,7 +297,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
             prev[n1] = 0.f;
             if (j0 + 1 < L) v[n1] = __ldg(reinterpret_cast<const float2 *>(xp + 32 * n1));
             else if (j0 < L) v[n1].x = __ldg(xp + 32 * n1);  // odd L: last tap alone
-            if (j0 < L) prev[n1] = __ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0));
+            if (!F512_PREV_SHFL && j0 < L) prev[n1] = __ldg(xp + 32 * n1 - (j0 > 0 ? 1 : 0));
           }
         }
       } else {  // a cut edge in this warp: per-tap reflection (layers.py:753-772); ~3 frames per cut
@@ -315,9 +309,11 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
             int64_t i = base + j0;
             if (!p.snip_edges) i = reflect_index(i, n);
             a = ld_sample<DT>(b.samples, xoff + i);
-            int64_t ip = base + (j0 > 0 ? j0 - 1 : 0);
-            if (!p.snip_edges) ip = reflect_index(ip, n);
-            pr = ld_sample<DT>(b.samples, xoff + ip);
+            if (!F512_PREV_SHFL) {
+              int64_t ip = base + (j0 > 0 ? j0 - 1 : 0);
+              if (!p.snip_edges) ip = reflect_index(ip, n);
+              pr = ld_sample<DT>(b.samples, xoff + ip);
+            }
           }
           if (j0 + 1 < L) {
             int64_t i = base + j0 + 1;
@@ -326,6 +322,15 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           }
           v[n1] = make_float2(a, c);
           prev[n1] = pr;
+        }
+      }
+      if (F512_PREV_SHFL) {  // the tap before (32 n1 + 2l) is the neighbour lane's odd tap: one shuffle instead of a load
+        float carry = v[0].x;  // lane 0, row 0: replicate-left (layers.py:166)
+#pragma unroll
+        for (int n1 = 0; n1 < NP; ++n1) {
+          const float up = __shfl_sync(F512_FULL, v[n1].y, (l + 15) & 15, 16);  // lane 0 receives lane 15's
+          prev[n1] = l == 0 ? carry : up;
+          carry = up;  // lane 15's odd tap of this row precedes lane 0's first tap of the next row
         }
       }
       // ---- DC removal (layers.py:155-157)
@@ -400,13 +405,9 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         const float sx = l == 0 ? zs0.x : zs.x, sy = l == 0 ? zs0.y : zs.y;
         const float2 cc = f2conj(make_float2(__shfl_sync(F512_FULL, sx, partner, 16), __shfl_sync(F512_FULL, sy, partner, 16)));
         const float2 E = f2add(zk, cc), O = f2sub(zk, cc);
-#if F512_SPLIT_TABLE
-        const float2 mit = f2mi(f2mul(O, s_tws[i * 16]));     // -i*T, T = W512^k * O from the [item][lane] table
-#else
         float2 wc = w32_const(2 * i);                 // W16^i; lane 0 needs W32^(own slot)
         if (i >= 5) { const float2 w0 = w32_const(kOwn0[i]); wc = l == 0 ? w0 : wc; }
         const float2 mit = f2mi(f2mul(f2mul(O, wc), w512l));  // -i*T
-#endif
         const float2 a = f2add(E, mit);               // 2*X[k]
         const float2 bq = f2sub(E, mit);              // 2*conj(X[256-k])
         float pa = fmaf(a.x, a.x, a.y * a.y), pb = fmaf(bq.x, bq.x, bq.y * bq.y);
@@ -631,17 +632,6 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
     };
     append(win2.data(), win2.size() * sizeof(float2));
     hst.t.off_tw1 = var.tws ? append(tw1.data(), tw1.size() * sizeof(float2)) : 0;
-    {  // split twiddles W512^k for the bin each (item, lane) handles: k = l + 32 i, lane 0: k = 16 * (its own slot)
-      static const int kOwn0[8] = {0, 2, 4, 6, 8, 1, 3, 5};
-      std::vector<float2> tws(8 * 16);
-      for (int i = 0; i < 8; ++i)
-        for (int l = 0; l < 16; ++l) {
-          const int k = l == 0 ? 16 * kOwn0[i] : l + 32 * i;
-          const double a = -2.0 * M_PI * (double)k / 512.0;
-          tws[i * 16 + l] = make_float2((float)cos(a), (float)sin(a));
-        }
-      hst.t.off_tws = append(tws.data(), tws.size() * sizeof(float2));
-    }
     std::vector<int> rdesc((size_t)std::max(rounds, 1) * 16 * 4, 0);  // per (round, lane): {first bin, trips, weight idx, 0}
     for (int j = 0; j < rounds; ++j)
       for (int l = 0; l < 16; ++l) {
