@@ -15,6 +15,7 @@
 #include "fast512x2.cuh"
 #include "fast256.cuh"
 #include "fast1024.cuh"
+#include "fast400.cuh"
 
 namespace {
 
@@ -52,6 +53,7 @@ struct b200feat_handle {
   FastX2Host fastx2;
   Fast256Host fast256;
   Fast1024Host fast1024;
+  Fast400Host fast400;
 };
 
 namespace {
@@ -225,11 +227,12 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   const bool fast512_ok = fastx2_supported(p) && fast512_supported(p);
   const bool fast256_ok = fast256_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
   const bool fast1024_ok = fast1024_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
-  const bool fast_ok = fast512_ok || fast256_ok || fast1024_ok;
+  const bool fast400_ok = fast400_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
+  const bool fast_ok = fast512_ok || fast256_ok || fast1024_ok || fast400_ok;
   const bool want_fast = desc->kernel == B200FEAT_KERNEL_FAST || desc->kernel == B200FEAT_KERNEL_FAST_X2;
   if (want_fast && !fast_ok) {
     cudaSetDevice(prev); b200feat_destroy(h);
-    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 256, 512 or 1024 (fast_x2: 512 only)");
+    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 256, 512, 1024 or frame_length = fft_length = 400 (fast_x2: 512 only)");
   }
   if (desc->kernel == B200FEAT_KERNEL_GENERIC || !fast_ok) h->kernel = B200FEAT_KERNEL_GENERIC;
   else if (desc->kernel == B200FEAT_KERNEL_FAST_X2) h->kernel = B200FEAT_KERNEL_FAST_X2;
@@ -258,6 +261,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   h->frames_per_tile = 1;
   if (h->kernel != B200FEAT_KERNEL_GENERIC) {
     if (h->plan.N == 256) rc = fast256_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast256);
+    else if (h->plan.N == 400) rc = fast400_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast400);
     else if (h->plan.N == 1024) rc = fast1024_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast1024);
     else if (h->kernel == B200FEAT_KERNEL_FAST_X2)
       rc = fastx2_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fastx2);
@@ -398,6 +402,9 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 256) {
     int rc = fast256_launch(h->plan, h->fast256, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast256 launch: ") + cudaGetErrorString((cudaError_t)rc));
+  } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 400) {
+    int rc = fast400_launch(h->plan, h->fast400, db, dt, h->sm_count, stream);
+    if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast400 launch: ") + cudaGetErrorString((cudaError_t)rc));
   } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 1024) {
     int rc = fast1024_launch(h->plan, h->fast1024, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast1024 launch: ") + cudaGetErrorString((cudaError_t)rc));

@@ -80,7 +80,8 @@ def main():
 
     # plans outside the N=512 fast path run on the generic kernel (mixed-radix Stockham in shared memory)
     for name, cfg, sr in (
-        ("fbank80 16k N=400 (round_to_power_of_two=False, radices 4,2,5,5)", lb.B200FbankConfig(round_to_power_of_two=False), 16000),
+        ("fbank80 16k N=400 (round_to_power_of_two=False; fast400, prime-factor 8x25)", lb.B200FbankConfig(round_to_power_of_two=False), 16000),
+        ("fbank80 16k N=400 forced generic (radices 4,2,5,5)", lb.B200FbankConfig(round_to_power_of_two=False, kernel="generic"), 16000),
         ("fbank40 8k N=256", lb.B200FbankConfig(sampling_rate=8000, num_filters=40), 8000),
         ("fbank80 24k N=1024 (fast1024)", lb.B200FbankConfig(sampling_rate=24000), 24000),
         ("fbank80 22.05k N=1024 (fast1024)", lb.B200FbankConfig(sampling_rate=22050), 22050),

@@ -410,3 +410,53 @@ def test_streaming_online_inference(i, m, x, y, r):
         assert online.shape == offline.shape
         # same frames, same arithmetic: the only difference is which load path (interior / edge) fetched the samples
         assert np.array_equal(online, offline)
+
+
+@pytest.mark.parametrize("feature,cfg", [
+    ("fbank", dict(round_to_power_of_two=False)),                                    # the "n_fft = 400" geometry
+    ("fbank", dict(round_to_power_of_two=False, num_filters=40, use_energy=True)),
+    ("fbank", dict(round_to_power_of_two=False, use_fft_mag=True, window_type="hamming", preemph_coeff=0.0, snip_edges=True)),
+    ("fbank", dict(round_to_power_of_two=False, raw_energy=False, use_energy=True, remove_dc_offset=False)),
+    ("mfcc", dict(round_to_power_of_two=False)),
+    ("mfcc", dict(round_to_power_of_two=False, use_energy=True, num_ceps=10)),
+    ("spectrogram", dict(round_to_power_of_two=False)),
+    ("log-spectrogram", dict(round_to_power_of_two=False, use_energy=True)),
+])
+def test_fast400_kernel_vs_oracle(feature, cfg):
+    """The N = L = 400 prime-factor kernel (round_to_power_of_two=False at 16 kHz) against the oracle and the generic
+    kernel on ragged lengths that hit the frame-count edges, plus int16 staging and the padded output mode."""
+    sr = 16000
+    ext = make(feature, cfg, kernel="fast")
+    assert ext.engine.kernel == "fast" and ext.plan.N == 400 and ext.plan.L == 400
+    gen = make(feature, cfg, kernel="generic")
+    rs = np.random.RandomState(11)
+    S, L = ext.plan.S, ext.plan.L
+    lens = [L, L + 1, 10 * S - 1, 10 * S + S // 2, 10 * S + S // 2 - 1, 16000, 16003, 40000, 333 * S, 57 * 2 * S]
+    xs = [(0.1 * rs.randn(m)).astype(np.float32) for m in lens]
+    xs[3][: len(xs[3]) // 2] *= 1e-4
+    xs[5] += 0.3  # DC offset
+    got = ext.extract_batch(xs, sr)
+    ocfg = oracle_cfg(feature, cfg)
+    for x, g in zip(xs, got):
+        ref = O.extract(x, ocfg)
+        truth = O.extract(x, ocfg, dtype=torch.float64)
+        assert g.shape == ref.shape
+        ok, msg = gate(g, ref, truth, feature, cfg.get("use_energy", False), cfg.get("use_fft_mag", False))
+        assert ok, msg
+    for a, b_ in zip(got, gen.extract_batch(xs, sr)):
+        np.testing.assert_allclose(a, b_, rtol=2e-4, atol=5e-4 if feature != "spectrogram" else 2e-3)
+    again = ext.extract_batch(xs, sr)
+    for a, b_ in zip(got, again):
+        assert np.array_equal(a, b_)  # deterministic
+    if feature == "fbank" and not cfg.get("use_energy"):
+        pcm = [np.clip(x * 32768, -32768, 32767).astype(np.int16) for x in xs]
+        i16 = ext.extract_batch(pcm, sr)
+        f32 = ext.extract_batch([q.astype(np.float32) / 32768.0 for q in pcm], sr)
+        for a, b_ in zip(i16, f32):
+            assert np.array_equal(a, b_)
+        feats, flens = ext.extract_batch_padded([torch.from_numpy(x) for x in xs], sr)
+        assert feats.shape[0] == len(xs) and flens.tolist() == [g.shape[0] for g in got]
+        fcpu = feats.cpu().numpy()
+        for i, g in enumerate(got):
+            assert np.array_equal(fcpu[i, : g.shape[0]], g)
+            assert np.all(fcpu[i, g.shape[0]:] == np.float32(LOG_EPSILON))
