@@ -12,7 +12,7 @@
 //      Z[(25 k1 + 176 r) mod 200] = row r, element k1                                   (CRT output map)
 //   5. real-FFT split: lane l takes element k1 = l of rows r = 0..12 and pairs it with element (8 - l) of row 25 - r
 //      (bins k and 200 - k), twiddle W400^k from a [row][lane] table;  |2X|^2 -> P[frame][bin] (201 bins);
-//   6. mel rounds of 8 filters on 128-bit loads, log, store (same epilogue as the other fast kernels).
+//   6. mel rounds of 16 filters (two per lane) on 128-bit loads, log, store.
 //
 // Replaces the same reference code as fast512.cuh (lhotse/features/kaldi/layers.py:151-186, :32-42, :565-578, :708-724,
 // framing :727-772) for Wav2LogFilterBank(round_to_power_of_two=False) & co (layers.py:264-265).
@@ -22,7 +22,8 @@
 #define F400_N 400
 #define F400_SLOTS 2                        // frames per quarter-warp per tile
 #define F400_XROW 10                        // float2 per exchange row (8 + 2 pad: 80 B)
-#define F400_XBUF (25 * F400_XROW)          // float2 per quarter-warp tile (2000 B; also holds the 400 raw samples)
+#define F400_XBUF 264                        // float2 per quarter-warp tile: 25 rows (2000 B; also holds the 400 raw samples),
+                                            // padded to 16 (mod 32) words so that neighbouring quarter-warps sit on disjoint banks
 #define F400_PBINS 204                      // floats per P row (201 bins + pad, multiple of 4)
 #define F400_PBUF (F400_PBINS * F400_SLOTS)
 #define F400_PTAIL 64
@@ -84,7 +85,7 @@ struct Fast400Tables {
   // one 16-byte-aligned blob (TMA bulk copy):
   //   [win2: 25*8 float2 (w[2m], w[2m+1]), m = (25 lane + 8 b) mod 200, indexed [b][lane]]
   //   [tws : 13*8 float2 W400^k, k = (25 lane + 176 r) mod 200, indexed [r][lane]]
-  //   [rdesc: rounds*8 int4 {first bin, trips, weight index, 0} | wdense: [row/4][lane][4] float]
+  //   [rdesc: rounds*16 int4 {first bin, trips, weight index, 0} | wdense: [row/4][16][4] float]
   const void *cblob;
   int cblob_bytes;
   int off_tws, off_rdesc, off_mw;
@@ -111,8 +112,8 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
   unsigned char *s_const = reinterpret_cast<unsigned char *>(pall + (size_t)QW * F400_PBUF + F400_PTAIL);
   const float2 *s_win = reinterpret_cast<const float2 *>(s_const);                 // [b][lane] window pairs (permuted)
   const float2 *s_tws = reinterpret_cast<const float2 *>(s_const + ft.off_tws);    // [r][lane] split twiddles
-  const int4 *s_rdesc = reinterpret_cast<const int4 *>(s_const + ft.off_rdesc);    // [round][lane]
-  const float4 *s_mw4 = reinterpret_cast<const float4 *>(s_const + ft.off_mw);     // [row / 4][lane][4]
+  const int4 *s_rdesc = reinterpret_cast<const int4 *>(s_const + ft.off_rdesc);    // [round][16 filters]
+  const float4 *s_mw4 = reinterpret_cast<const float4 *>(s_const + ft.off_mw);     // [row / 4][16][4]
   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_const + ft.cblob_bytes);
   float2 *X = xall + (size_t)qw * F400_XBUF;
   float *S = reinterpret_cast<float *>(X);   // the same tile first holds the frame's raw samples
@@ -291,35 +292,40 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(X);  // the exchange tile is idle during the epilogue
+      // rounds of 16 filters, two per lane (l and l + 8): the per-round overhead is shared by 2 filters x 2 frames
       for (int j = 0; j < ft.mel_rounds; ++j) {
-        const int m = l + 8 * j;
-        const int4 rd = s_rdesc[j * 8 + l];
-        const float4 *pp = reinterpret_cast<const float4 *>(P + rd.x);
-        const float4 *wp = s_mw4 + rd.z;
-        float acc[F400_SLOTS];
+        const int4 ra = s_rdesc[j * 16 + l], rb = s_rdesc[j * 16 + l + 8];
+        const float4 *pa = reinterpret_cast<const float4 *>(P + ra.x), *pb = reinterpret_cast<const float4 *>(P + rb.x);
+        const float4 *wa = s_mw4 + ra.z, *wb = s_mw4 + rb.z;
+        float acc[2][F400_SLOTS];
 #pragma unroll
-        for (int f = 0; f < F400_SLOTS; ++f) acc[f] = 0.f;
+        for (int f = 0; f < F400_SLOTS; ++f) acc[0][f] = acc[1][f] = 0.f;
 #pragma unroll 1
-        for (int i = rd.y; i > 0; i -= 4, ++pp, wp += 8) {
-          const float4 wi = *wp;
+        for (int i = ra.y; i > 0; i -= 4, ++pa, ++pb, wa += 16, wb += 16) {
+          const float4 ua = *wa, ub = *wb;
 #pragma unroll
           for (int f = 0; f < F400_SLOTS; ++f) {
-            const float4 pv = pp[f * (F400_PBINS / 4)];
-            acc[f] = fmaf(pv.w, wi.w, fmaf(pv.z, wi.z, fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]))));
+            const float4 qa = pa[f * (F400_PBINS / 4)], qb = pb[f * (F400_PBINS / 4)];
+            acc[0][f] = fmaf(qa.w, ua.w, fmaf(qa.z, ua.z, fmaf(qa.y, ua.y, fmaf(qa.x, ua.x, acc[0][f]))));
+            acc[1][f] = fmaf(qb.w, ub.w, fmaf(qb.z, ub.z, fmaf(qb.y, ub.y, fmaf(qb.x, ub.x, acc[1][f]))));
           }
         }
-        if (m < p.M) {
-          float r[F400_SLOTS];
 #pragma unroll
-          for (int f = 0; f < F400_SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[f], p.mel_floor));
-          if (p.feature == B200FEAT_FBANK) {
-            float *orow = out + m + shift;
+        for (int h = 0; h < 2; ++h) {
+          const int m = l + 8 * h + 16 * j;
+          if (m < p.M) {
+            float r[F400_SLOTS];
 #pragma unroll
-            for (int f = 0; f < F400_SLOTS; ++f)
-              if (f < nvalid) orow[(int64_t)f * p.F] = r[f];
-          } else {
+            for (int f = 0; f < F400_SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[h][f], p.mel_floor));
+            if (p.feature == B200FEAT_FBANK) {
+              float *orow = out + m + shift;
 #pragma unroll
-            for (int f = 0; f < F400_SLOTS; ++f) mlog[f * Mpad + m] = r[f];
+              for (int f = 0; f < F400_SLOTS; ++f)
+                if (f < nvalid) orow[(int64_t)f * p.F] = r[f];
+            } else {
+#pragma unroll
+              for (int f = 0; f < F400_SLOTS; ++f) mlog[f * Mpad + m] = r[f];
+            }
           }
         }
       }
@@ -386,7 +392,7 @@ static inline int fast400_prepare(DevPlan &p, const std::vector<float> &bank, st
       const double a = -2.0 * M_PI * (double)k / 400.0;
       tws[r * 8 + l] = make_float2((float)cos(a), (float)sin(a));
     }
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 8, 4);
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, 4);  // 16 filters per round, two per lane
   if (mr.max_reach > F400_PBINS) return B200FEAT_EUNSUPPORTED;
   hst.t.mel_rounds = mr.rounds;
   int rc;
@@ -400,11 +406,11 @@ static inline int fast400_prepare(DevPlan &p, const std::vector<float> &bank, st
     };
     append(win2.data(), win2.size() * sizeof(float2));
     hst.t.off_tws = append(tws.data(), tws.size() * sizeof(float2));
-    std::vector<int> rdesc((size_t)std::max(mr.rounds, 1) * 8 * 4, 0);
+    std::vector<int> rdesc((size_t)std::max(mr.rounds, 1) * 16 * 4, 0);
     for (int j = 0; j < mr.rounds; ++j)
-      for (int l = 0; l < 8; ++l) {
-        int *d = &rdesc[((size_t)j * 8 + l) * 4];
-        d[0] = mr.rstart[j * 8 + l]; d[1] = mr.rlen[j]; d[2] = mr.rrow[j] * 2 + l;  // float4 index: (row / 4) * 8 + lane
+      for (int l = 0; l < 16; ++l) {
+        int *d = &rdesc[((size_t)j * 16 + l) * 4];
+        d[0] = mr.rstart[j * 16 + l]; d[1] = mr.rlen[j]; d[2] = mr.rrow[j] * 4 + l;  // float4 index: (row / 4) * 16 + column
       }
     hst.t.off_rdesc = append(rdesc.data(), rdesc.size() * sizeof(int));
     hst.t.off_mw = append(mr.wdense.data(), mr.wdense.size() * sizeof(float));

@@ -11,7 +11,8 @@ kernel = sys.argv[2] if len(sys.argv) > 2 else "auto"
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 6
 n = 160000
 dev = torch.device("cuda", 0)
-plan = lb.build_plan("fbank", lb.B200FbankConfig())
+geom = sys.argv[4] if len(sys.argv) > 4 else "n512"   # n512 | n400 (round_to_power_of_two=False)
+plan = lb.build_plan("fbank", lb.B200FbankConfig(round_to_power_of_two=(geom != "n400")))
 eng = Engine(plan, device=dev, kernel=kernel)
 torch.manual_seed(0)
 x = 0.1 * torch.randn(B * n, device=dev)

@@ -18,8 +18,8 @@ from lhotse_b200.engine import Engine
 B, reps, feature = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 n = 160000
 dev = torch.device("cuda", 0)
-cfgs = {"fbank": lb.B200FbankConfig(), "mfcc": lb.B200MfccConfig(num_ceps=13, num_filters=23), "spectrogram": lb.B200SpectrogramConfig()}
-eng = Engine(lb.build_plan(feature, cfgs[feature]), device=dev, kernel="fast")
+cfgs = {"fbank": lb.B200FbankConfig(), "fbank400": lb.B200FbankConfig(round_to_power_of_two=False), "mfcc": lb.B200MfccConfig(num_ceps=13, num_filters=23), "spectrogram": lb.B200SpectrogramConfig()}
+eng = Engine(lb.build_plan("fbank" if feature.startswith("fbank") else feature, cfgs[feature]), device=dev, kernel="fast")
 torch.manual_seed(0)
 x = 0.1 * torch.randn(B * n, device=dev)
 lens, offs = [n] * B, [i * n for i in range(B)]
