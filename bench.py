@@ -230,6 +230,8 @@ def run_b200(args):
     rank, world, local = lbd.init_distributed()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep this rank's threads and its pinned staging buffers on the GPU's own NUMA node
+    numa_node = lbd.bind_host_to_gpu_numa(local)
 
     cfg = lb.B200FbankConfig(device=f"cuda:{local}", kernel=args.kernel)
     plan = lb.build_plan("fbank", cfg)
@@ -323,7 +325,8 @@ def run_b200(args):
             "config": {"workload": f"Fbank-80 16kHz 25ms/10ms N=512 (L=400,S=160), {B} x {args.cut_seconds:g}s cuts per GPU per step (BASELINE configs[1])",
                        "cuts_per_gpu_per_step": B, "frames_per_gpu_per_step": frames, "kernel": eng.kernel,
                        "parallelism": f"dp{world} (cuts sharded per rank, no data-path collective)",
-                       "l2_policy": f"inputs {B * nsamp * 4 / 2**20:.0f} MiB + outputs {frames * 320 / 2**20:.0f} MiB per step > 126 MiB L2"},
+                       "l2_policy": f"inputs {B * nsamp * 4 / 2**20:.0f} MiB + outputs {frames * 320 / 2**20:.0f} MiB per step > 126 MiB L2",
+                       "host_numa_node": numa_node},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Be * nsamp * 4,
                     "d2h_bytes_per_step": d2h_bytes, "cuts_per_step": Be, "steps": args.e2e_steps,
                     "api": "B200Fbank.extract_batch(numpy (B, n) float32 in pinned memory) -> numpy (B, T, 80); C ABI b200feat_extract_host underneath"},

@@ -42,6 +42,52 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def gpu_numa_node(device_index: int) -> Optional[int]:
+    """NUMA node of a CUDA device (sysfs `numa_node` of its PCI function), or None when the platform does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers it allocates
+    next (first touch) and the threads that fill them are local to the GPU's PCIe root.  One process per GPU is the
+    deployment model (torchrun), so this is a per-rank decision.  On a two-socket box with 8 GPUs the host-to-host rate is
+    bound by host memory traffic, and remote (cross-socket) pinned buffers halve it.  Returns the node, or None when
+    nothing was changed (single node, no permission, unknown topology).  `B200FEAT_NO_NUMA_BIND=1` disables it."""
+    if os.environ.get("B200FEAT_NO_NUMA_BIND") == "1" or not hasattr(os, "sched_setaffinity"):
+        return None
+    node = gpu_numa_node(device_index)
+    if node is None:
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set(_parse_cpulist(f.read()))
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        if not target or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        return node
+    except (OSError, ValueError):
+        return None
+
+
 def shard_slice(items: Sequence[T], rank: int, world: int) -> List[T]:
     """rank::world striding — identical to LazySlicer(k=rank, n=world)."""
     return list(items[rank::world])

@@ -69,3 +69,14 @@ def test_single_process_noops():
     assert lbd.broadcast_plan_tables(plan) is plan
     assert lbd.all_reduce_stats([1.0, 2.0]) == [1.0, 2.0]
     assert lbd.shard_slice(list(range(10)), 1, 4) == [1, 5, 9]
+
+
+def test_numa_binding_helpers_are_safe_without_gpu():
+    """`bind_host_to_gpu_numa` must never raise: no GPU / no sysfs / single node all mean "leave the process alone"."""
+    from lhotse_b200 import dist as lbd
+    assert lbd._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert lbd._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    assert lbd.bind_host_to_gpu_numa(0) is None or isinstance(lbd.bind_host_to_gpu_numa(0), int)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
