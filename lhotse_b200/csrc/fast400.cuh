@@ -20,7 +20,9 @@
 #include "fast256.cuh"
 
 #define F400_N 400
+#ifndef F400_SLOTS
 #define F400_SLOTS 2                        // frames per quarter-warp per tile
+#endif
 #define F400_XROW 10                        // float2 per exchange row (8 + 2 pad: 80 B)
 #define F400_XBUF 264                        // float2 per quarter-warp tile: 25 rows (2000 B; also holds the 400 raw samples),
                                             // padded to 16 (mod 32) words so that neighbouring quarter-warps sit on disjoint banks
@@ -358,7 +360,9 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
 }
 
 // ---------------------------------------------------------------------------------------------- host
+#ifndef F400_WARPS
 #define F400_WARPS 7
+#endif
 struct Fast400Host {
   Fast400Tables t;
   size_t smem;
