@@ -460,3 +460,51 @@ def test_fast400_kernel_vs_oracle(feature, cfg):
         for i, g in enumerate(got):
             assert np.array_equal(fcpu[i, : g.shape[0]], g)
             assert np.all(fcpu[i, g.shape[0]:] == np.float32(LOG_EPSILON))
+
+
+def _fuzz_cases():
+    rs = np.random.RandomState(2024)
+    cases = []
+    geoms = [(16000, 0.025, 0.01, True), (16000, 0.025, 0.01, False), (8000, 0.025, 0.01, True), (24000, 0.025, 0.01, True),
+             (22050, 0.025, 0.01, True), (16000, 0.02, 0.01, True), (16000, 0.032, 0.016, True), (44100, 0.02, 0.01, True),
+             (16000, 0.05, 0.0125, True), (8000, 0.032, 0.008, True)]
+    for i in range(24):
+        sr, fl, fs, pow2 = geoms[rs.randint(len(geoms))]
+        feature = ["fbank", "fbank", "mfcc", "spectrogram", "log-spectrogram"][rs.randint(5)]
+        cfg = dict(sampling_rate=sr, frame_length=fl, frame_shift=fs, round_to_power_of_two=pow2,
+                   window_type=["povey", "hanning", "hamming", "rectangular", "blackman"][rs.randint(5)],
+                   preemph_coeff=[0.97, 0.0, 0.5][rs.randint(3)], remove_dc_offset=bool(rs.randint(2)),
+                   snip_edges=bool(rs.randint(4) == 0), use_energy=bool(rs.randint(3) == 0), raw_energy=bool(rs.randint(2)),
+                   use_fft_mag=bool(rs.randint(4) == 0))
+        if feature in ("fbank", "mfcc"):
+            cfg.update(num_filters=int([4, 5, 23, 40, 80, 128][rs.randint(6)]), low_freq=float([20.0, 0.0, 100.0][rs.randint(3)]),
+                       high_freq=float([-400.0, 0.0, -1000.0][rs.randint(3)]))
+        if feature == "mfcc":
+            cfg.update(num_ceps=int(min(cfg["num_filters"], [13, 20, 2][rs.randint(3)])), cepstral_lifter=int([22, 10][rs.randint(2)]))
+        cases.append((i, feature, cfg))
+    return cases
+
+
+@pytest.mark.parametrize("i,feature,cfg", _fuzz_cases(), ids=[f"{i}-{f}" for i, f, _ in _fuzz_cases()])
+def test_random_configs_auto_kernel_vs_oracle(i, feature, cfg):
+    """Seeded random walk over the config space (geometry, window, flags, mel bank shape) through AUTO kernel selection —
+    whichever kernel the plan lands on, and the generic kernel, must agree with the oracle and with each other."""
+    sr = cfg["sampling_rate"]
+    ext = make(feature, cfg)
+    rs = np.random.RandomState(100 + i)
+    S, L = ext.plan.S, ext.plan.L
+    lens = [L + 3 * S, 17 * S + 5, 40 * S + S // 2, 123 * S]
+    xs = [(0.1 * rs.randn(m)).astype(np.float32) for m in lens]
+    xs[1] += 0.05
+    ocfg = oracle_cfg(feature, cfg)
+    outs = {}
+    for kern in kernels_for(ext):
+        e = make(feature, cfg, kernel=kern)
+        got = e.extract_batch(xs, sr)
+        outs[kern] = got
+        for x, g in zip(xs, got):
+            ref = O.extract(x, ocfg)
+            truth = O.extract(x, ocfg, dtype=torch.float64)
+            assert g.shape == ref.shape, (kern, g.shape, ref.shape)
+            ok, msg = gate(g, ref, truth, feature, cfg["use_energy"], cfg["use_fft_mag"])
+            assert ok, f"{kern}: {msg}"
