@@ -127,10 +127,11 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
     const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED ? (int64_t)(b.batch_first + cut) * b.max_frames + t0
                                                            : __ldg(b.row_off + cut) + t0;
     float le[SLOTS];
+#pragma unroll
+    for (int k = 0; k < SLOTS; ++k) le[k] = 0.f;
 
 #pragma unroll 1
     for (int f = 0; f < SLOTS; ++f) {
-      le[f] = 0.f;
       const int64_t t = t0 + f;
       if (t >= T) continue;  // warp-uniform
       const int64_t base = t * p.S - (p.snip_edges ? 0 : p.pad_left);
@@ -145,11 +146,9 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           v[n1] = pv[n1] = make_float2(0.f, 0.f);
           if (ja < L) {
             v[n1].x = ld_sample<DT>(b.samples, x0 + 64 * n1);
-            pv[n1].x = ld_sample<DT>(b.samples, x0 + 64 * n1 - (ja > 0 ? 1 : 0));
           }
           if (ja + 2 < L) {
             v[n1].y = ld_sample<DT>(b.samples, x0 + 64 * n1 + 2);
-            pv[n1].y = ld_sample<DT>(b.samples, x0 + 64 * n1 + 1);
           }
         }
       } else {  // cut edge: per-tap reflection (layers.py:753-772)
@@ -158,17 +157,28 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           const int ja = 64 * n1 + 4 * l + h;
           v[n1] = pv[n1] = make_float2(0.f, 0.f);
           if (ja < L) {
-            int64_t i = base + ja, ip = base + (ja > 0 ? ja - 1 : 0);
-            if (!p.snip_edges) { i = reflect_index(i, n); ip = reflect_index(ip, n); }
+            int64_t i = base + ja;
+            if (!p.snip_edges) i = reflect_index(i, n);
             v[n1].x = ld_sample<DT>(b.samples, xoff + i);
-            pv[n1].x = ld_sample<DT>(b.samples, xoff + ip);
           }
           if (ja + 2 < L) {
-            int64_t i = base + ja + 2, ip = base + ja + 1;
-            if (!p.snip_edges) { i = reflect_index(i, n); ip = reflect_index(ip, n); }
+            int64_t i = base + ja + 2;
+            if (!p.snip_edges) i = reflect_index(i, n);
             v[n1].y = ld_sample<DT>(b.samples, xoff + i);
-            pv[n1].y = ld_sample<DT>(b.samples, xoff + ip);
           }
+        }
+      }
+      {  // the taps before ja and ja + 2 live in neighbouring lanes: two shuffles instead of two more loads
+        //   y[ja - 1]: h = 1 -> (l, 0).x ; h = 0 -> (l - 1, 1).y, and for l = 0 the previous row's (15, 1).y
+        //   y[ja + 1]: h = 0 -> (l, 1).x ; h = 1 -> (l, 0).y
+        float carry = v[0].x;  // lane (0, 0), row 0: replicate-left (layers.py:166)
+        const int src1 = h ? lane - 16 : 16 + ((l + 15) & 15);
+#pragma unroll
+        for (int n1 = 0; n1 < NP; ++n1) {
+          const float r1 = __shfl_sync(F512_FULL, h ? v[n1].y : v[n1].x, src1);
+          const float r2 = __shfl_xor_sync(F512_FULL, h ? v[n1].x : v[n1].y, 16);
+          pv[n1] = make_float2(lane == 0 ? carry : r1, r2);
+          carry = r1;
         }
       }
       // ---- DC removal over the whole frame (both halves), energy, pre-emphasis, window (layers.py:155-170)
@@ -194,7 +204,11 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           v[n1] = make_float2(0.f, 0.f);
         }
       }
-      if (p.use_energy) le[f] = log_energy_value(p, warp_sum(e));
+      if (p.use_energy) {  // le[] stays in registers: no dynamic indexing
+        const float lev = log_energy_value(p, warp_sum(e));
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) le[k] = (f == k) ? lev : le[k];
+      }
 
       // ---- 512-point real FFT of this half's sub-sequence: stage 1, transpose, stage 2 (as in fast512.cuh)
       dft16(v);
@@ -259,7 +273,10 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         for (int k = lane; k < p.K; k += 32) {
           float x = P[f * F1K_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
-          if (k == 0 && p.use_energy) x = le[f];
+          if (k == 0 && p.use_energy) {
+#pragma unroll
+            for (int g = 0; g < SLOTS; ++g) x = (f == g) ? le[g] : x;
+          }
           o[k] = x;
         }
       }
@@ -275,13 +292,14 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         float acc[SLOTS];
 #pragma unroll
         for (int f = 0; f < SLOTS; ++f) acc[f] = 0.f;
-        const float4 *w4 = reinterpret_cast<const float4 *>(wj - lane) + lane;  // [row / 4][lane][4]
+        const float4 *wp = reinterpret_cast<const float4 *>(wj - lane) + lane;  // [row / 4][lane][4]
+        const float4 *pp = reinterpret_cast<const float4 *>(Pj);
 #pragma unroll 1
-        for (int i = 0; i < len; i += 4) {
-          const float4 wi = w4[i * 8];
+        for (int i = len; i > 0; i -= 4, ++pp, wp += 32) {
+          const float4 wi = *wp;
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) {
-            const float4 pv = *reinterpret_cast<const float4 *>(Pj + f * F1K_PBINS + i);
+            const float4 pv = pp[f * (F1K_PBINS / 4)];
             acc[f] = fmaf(pv.w, wi.w, fmaf(pv.z, wi.z, fmaf(pv.y, wi.y, fmaf(pv.x, wi.x, acc[f]))));
           }
         }

@@ -122,10 +122,11 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
     const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED ? (int64_t)(b.batch_first + cut) * b.max_frames + t0
                                                            : __ldg(b.row_off + cut) + t0;
     float le[F256_SLOTS];
+#pragma unroll
+    for (int k = 0; k < F256_SLOTS; ++k) le[k] = 0.f;
 
 #pragma unroll 1
     for (int f = 0; f < F256_SLOTS; ++f) {
-      le[f] = 0.f;
       if (!__any_sync(F512_FULL, t0 + f < T)) continue;
       const int64_t t = min(max(t0 + f, (int64_t)0), T - 1);  // out-of-range quarters redo the last frame (not stored)
       const int64_t base = t * p.S - (p.snip_edges ? 0 : p.pad_left);
@@ -146,7 +147,6 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
             } else if (j0 < L) {
               v[n1].x = (float)__ldg(xp + 16 * n1) * (1.0f / 32768.0f);
             }
-            if (j0 < L) prev[n1] = (float)__ldg(xp + 16 * n1 - (j0 > 0 ? 1 : 0)) * (1.0f / 32768.0f);
           }
         } else {
           const float *xp = reinterpret_cast<const float *>(b.samples) + (xoff + base + 2 * l);
@@ -157,7 +157,6 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
             prev[n1] = 0.f;
             if (j0 + 1 < L) v[n1] = __ldg(reinterpret_cast<const float2 *>(xp + 16 * n1));
             else if (j0 < L) v[n1].x = __ldg(xp + 16 * n1);
-            if (j0 < L) prev[n1] = __ldg(xp + 16 * n1 - (j0 > 0 ? 1 : 0));
           }
         }
       } else {  // a cut edge in this warp: per-tap reflection (layers.py:753-772)
@@ -169,9 +168,6 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
             int64_t i = base + j0;
             if (!p.snip_edges) i = reflect_index(i, n);
             a = ld_sample<DT>(b.samples, xoff + i);
-            int64_t ip = base + (j0 > 0 ? j0 - 1 : 0);
-            if (!p.snip_edges) ip = reflect_index(ip, n);
-            pr = ld_sample<DT>(b.samples, xoff + ip);
           }
           if (j0 + 1 < L) {
             int64_t i = base + j0 + 1;
@@ -180,6 +176,15 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
           }
           v[n1] = make_float2(a, c);
           prev[n1] = pr;
+        }
+      }
+      {  // the tap before (16 n1 + 2l) is the neighbour lane's odd tap: one shuffle instead of a second load
+        float carry = v[0].x;  // lane 0, row 0: replicate-left (layers.py:166)
+#pragma unroll
+        for (int n1 = 0; n1 < NP; ++n1) {
+          const float up = __shfl_sync(F512_FULL, v[n1].y, (l + 7) & 7, 8);  // lane 0 receives lane 7's
+          prev[n1] = l == 0 ? carry : up;
+          carry = up;  // lane 7's odd tap of this row precedes lane 0's first tap of the next row
         }
       }
       // ---- DC removal, energy, pre-emphasis, window (layers.py:155-170)
@@ -205,7 +210,11 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
           v[n1] = make_float2(0.f, 0.f);
         }
       }
-      if (p.use_energy) le[f] = log_energy_value(p, qw_sum(e));
+      if (p.use_energy) {  // le[] stays in registers: no dynamic indexing
+        const float lev = log_energy_value(p, qw_sum(e));
+#pragma unroll
+        for (int k = 0; k < F256_SLOTS; ++k) le[k] = (f == k) ? lev : le[k];
+      }
 
       // ---- stage 1: radix-16 over n1, twiddle W128^(l*k1), 16x8 transpose
       dft16(v);
@@ -281,7 +290,10 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
         for (int k = l; k < p.K; k += 8) {
           float x = P[f * F256_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
-          if (k == 0 && p.use_energy) x = le[f];
+          if (k == 0 && p.use_energy) {
+#pragma unroll
+            for (int q = 0; q < F256_SLOTS; ++q) x = (f == q) ? le[q] : x;
+          }
           o[k] = x;
         }
       }
