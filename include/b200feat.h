@@ -11,6 +11,7 @@
  *   - lhotse/features/kaldi/extractors.py:297 Spectrogram  (.extract :318)
  *   - lhotse/features/kaldi/extractors.py:407 LogSpectrogram (.extract :428)
  *   - lhotse/features/kaldi/extractors.py:485 _extract_batch (pad, forward, trim)
+ *   - lhotse/features/whisper_fbank.py:16-84  log_mel_spectrogram, :103 WhisperFbank (.extract :138)
  *   - lhotse/features/kaldi/layers.py:151-186, :309-320, :392-402, :461-473, :565-578, :708-724
  *     (the arithmetic), :727-772 (framing), lhotse/utils.py:424-434 (frame-count contract)
  *
@@ -51,6 +52,10 @@ extern "C" {
 #define B200FEAT_MFCC 1            /* Wav2MFCC, layers.py:581 */
 #define B200FEAT_SPECTROGRAM 2     /* Wav2Spec, layers.py:336 */
 #define B200FEAT_LOG_SPECTROGRAM 3 /* Wav2LogSpec, layers.py:405 */
+#define B200FEAT_WHISPER_FBANK 4   /* WhisperFbank / log_mel_spectrogram, lhotse/features/whisper_fbank.py:16-84:
+                                      torch.stft(center=True) framing, log10(max(mel, mel_floor)), clamp to the cut's
+                                      maximum - 8, (x + 4) / 4; rows beyond the stft's n/S frames are 0 (:73-80).
+                                      Two launches per batch: the fused kernel (+ per-cut max) and a normalise pass. */
 
 /* sample dtypes accepted by the kernels */
 #define B200FEAT_F32 0 /* float32 in [-1, 1] — what lhotse hands to extract() */
@@ -64,6 +69,12 @@ extern "C" {
 /* log-energy conventions (SURVEY.md §8a "semantic differences") */
 #define B200FEAT_ENERGY_LHOTSE 0 /* max(log(sum + 1e-15), log(floor)) iff floor > 0; layers.py:859-870 */
 #define B200FEAT_ENERGY_KALDI 1  /* max(log(max(sum, eps32)), log(floor)) iff floor != 0; torchaudio kaldi.py:116-122 */
+
+/* framing / padding conventions (b200feat_plan_desc.pad_mode) */
+#define B200FEAT_PAD_KALDI 0  /* lhotse/Kaldi: frame t starts at t*S - (L-S)/2, edges mirrored WITH the edge sample
+                                 (x[-1] = x[0]); T = (n + S/2) / S; layers.py:753-772 */
+#define B200FEAT_PAD_CENTER 1 /* torch.stft(center=True, pad_mode="reflect"): frame t starts at t*S - N/2, edges mirrored
+                                 WITHOUT the edge sample (x[-1] = x[1]); needs n > N/2; whisper_fbank.py:62 */
 
 /* kernel selection (b200feat_plan_desc.kernel) */
 #define B200FEAT_KERNEL_AUTO 0
@@ -87,7 +98,7 @@ typedef struct b200feat_plan_desc {
   int32_t energy_style; /* B200FEAT_ENERGY_* */
   int32_t use_lifter;   /* multiply cepstra by lifter[] */
   int32_t kernel;       /* B200FEAT_KERNEL_* */
-  int32_t reserved0;
+  int32_t pad_mode;     /* B200FEAT_PAD_* (B200FEAT_PAD_CENTER is accepted with B200FEAT_WHISPER_FBANK only) */
   float preemph_coeff;  /* 0 disables, layers.py:165 */
   float energy_floor;   /* linear-domain floor (EPSILON = 1e-10 by default) */
   float mel_floor;      /* clamp before log for fbank/mfcc: finfo(float32).eps, layers.py:572 */
@@ -110,7 +121,8 @@ typedef struct b200feat_batch_totals {
   int64_t max_frames;    /* T_max */
   int64_t total_tiles;   /* work items of the selected kernel */
   int64_t span_samples;  /* elements the sample buffer must hold (last offset + last length) */
-  int64_t out_floats;    /* floats the output buffer must hold for the chosen out_mode */
+  int64_t out_floats;    /* floats the output buffer must hold for the chosen out_mode; for B200FEAT_WHISPER_FBANK this
+                            includes B trailing scratch floats (the per-cut maxima) after the feature rows */
   int64_t meta_words;    /* int64 words of meta actually written (what must reach the device) */
 } b200feat_batch_totals;
 
@@ -134,7 +146,7 @@ const char *b200feat_last_error(const b200feat_handle *h);
 /* T for a cut of n samples (layers.py:747-753); B200FEAT_ESHORT if it cannot be framed
  * (n too short for a single reflection — the reference raises on those). */
 int64_t b200feat_num_frames(const b200feat_handle *h, int64_t num_samples);
-/* F: M (+1 with use_energy) for fbank, C for mfcc, N/2+1 for the spectrogram kinds. */
+/* F: M (+1 with use_energy) for fbank, M for whisper-fbank, C for mfcc, N/2+1 for the spectrogram kinds. */
 int32_t b200feat_feature_dim(const b200feat_handle *h);
 /* B200FEAT_KERNEL_GENERIC or B200FEAT_KERNEL_FAST — what AUTO resolved to. */
 int32_t b200feat_kernel_kind(const b200feat_handle *h);

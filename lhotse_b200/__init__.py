@@ -10,6 +10,8 @@ from .extractors import (  # noqa: F401
     B200MfccConfig,
     B200Spectrogram,
     B200SpectrogramConfig,
+    B200WhisperFbank,
+    B200WhisperFbankConfig,
     from_reference_config,
     install_as_default,
 )

@@ -91,8 +91,11 @@ std::vector<int> factorize(int n) {
   return f;
 }
 
+// Output rows of a cut.  For whisper-fbank this is compute_num_frames_from_samples (whisper_fbank.py:73-80, utils.py:424):
+// the stft itself yields n / S frames (1 + n / S, last one dropped, :62-63); a missing last row is a zero row.
 int64_t frames_for(const b200feat_plan_desc &d, int64_t n) {
   const int64_t L = d.frame_length, S = d.frame_shift;
+  if (d.feature == B200FEAT_WHISPER_FBANK) return (n + S / 2) / S;
   if (d.snip_edges) return n < L ? 0 : 1 + (n - L) / S;
   return (n + S / 2) / S;
 }
@@ -100,6 +103,7 @@ int64_t frames_for(const b200feat_plan_desc &d, int64_t n) {
 // The reference can frame a cut only if one reflection per side suffices (layers.py:757-764).
 bool framable(const b200feat_plan_desc &d, int64_t n, int64_t T) {
   if (T <= 0) return false;
+  if (d.pad_mode == B200FEAT_PAD_CENTER) return n > d.fft_length / 2;  // torch's reflect padding needs pad < n
   if (d.snip_edges) return true;
   const int64_t L = d.frame_length, S = d.frame_shift;
   const int64_t left = (L - S) / 2;
@@ -123,8 +127,15 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   const int L = desc->frame_length, S = desc->frame_shift, N = desc->fft_length;
   if (L <= 0 || S <= 0 || N < L || N < 2) return fail(nullptr, B200FEAT_EINVAL, "bad L/S/N");
   if (!window) return fail(nullptr, B200FEAT_EINVAL, "window table is required");
-  const bool mel = desc->feature == B200FEAT_FBANK || desc->feature == B200FEAT_MFCC;
-  if (desc->feature < 0 || desc->feature > 3) return fail(nullptr, B200FEAT_EINVAL, "bad feature kind");
+  const bool whisper = desc->feature == B200FEAT_WHISPER_FBANK;
+  const bool mel = desc->feature == B200FEAT_FBANK || desc->feature == B200FEAT_MFCC || whisper;
+  if (desc->feature < 0 || desc->feature > 4) return fail(nullptr, B200FEAT_EINVAL, "bad feature kind");
+  if (desc->pad_mode != B200FEAT_PAD_KALDI && desc->pad_mode != B200FEAT_PAD_CENTER)
+    return fail(nullptr, B200FEAT_EINVAL, "bad pad_mode");
+  if ((desc->pad_mode == B200FEAT_PAD_CENTER) != whisper)
+    return fail(nullptr, B200FEAT_EINVAL, "pad_mode CENTER goes with the whisper-fbank kind (and only with it)");
+  if (whisper && (desc->snip_edges || desc->use_energy || desc->use_fft_mag || desc->mel_floor <= 0.f))
+    return fail(nullptr, B200FEAT_EINVAL, "whisper-fbank: snip_edges / use_energy / use_fft_mag must be off, mel_floor > 0");
   if (mel && (desc->num_filters <= 0 || !mel_bank)) return fail(nullptr, B200FEAT_EINVAL, "mel bank required");
   if (desc->feature == B200FEAT_MFCC && (desc->num_ceps <= 0 || !dct))
     return fail(nullptr, B200FEAT_EINVAL, "dct required for mfcc");
@@ -157,7 +168,9 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   p.C = desc->feature == B200FEAT_MFCC ? desc->num_ceps : 0;
   p.packed = (N % 2 == 0);
   p.Nc = p.packed ? N / 2 : N;
-  p.pad_left = (L - S) / 2;
+  p.pad_mode = desc->pad_mode;
+  p.whisper = whisper ? 1 : 0;
+  p.pad_left = desc->pad_mode == B200FEAT_PAD_CENTER ? N / 2 : (L - S) / 2;
   p.snip_edges = desc->snip_edges; p.remove_dc = desc->remove_dc_offset;
   p.use_energy = desc->use_energy; p.raw_energy = desc->raw_energy; p.use_mag = desc->use_fft_mag;
   p.energy_style = desc->energy_style; p.use_lifter = desc->use_lifter;
@@ -169,6 +182,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   p.mel_floor = desc->mel_floor; p.log_spec_eps = desc->log_spec_eps;
   switch (desc->feature) {
     case B200FEAT_FBANK: p.F = p.M + (desc->use_energy ? 1 : 0); break;
+    case B200FEAT_WHISPER_FBANK: p.F = p.M; break;
     case B200FEAT_MFCC: p.F = p.C; break;
     default: p.F = p.K;
   }
@@ -224,9 +238,10 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   if (desc->use_lifter) UP(upload(h, h->h_lifter.data(), h->h_lifter.size(), &p.lifter));
 
   // ---- kernel selection
-  const bool fast512_ok = fastx2_supported(p) && fast512_supported(p);
-  const bool fast256_ok = fast256_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
-  const bool fast1024_ok = fast1024_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
+  // the whisper-fbank epilogue / centre padding exist in the generic and the fast400 kernels only
+  const bool fast512_ok = !whisper && fastx2_supported(p) && fast512_supported(p);
+  const bool fast256_ok = !whisper && fast256_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
+  const bool fast1024_ok = !whisper && fast1024_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
   const bool fast400_ok = fast400_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
   const bool fast_ok = fast512_ok || fast256_ok || fast1024_ok || fast400_ok;
   const bool want_fast = desc->kernel == B200FEAT_KERNEL_FAST || desc->kernel == B200FEAT_KERNEL_FAST_X2;
@@ -372,6 +387,7 @@ int b200feat_plan_batch(const b200feat_handle *hc, const int64_t *num_samples,
   tot->meta_words = words;
   tot->total_rows = rows; tot->max_frames = tmax; tot->total_tiles = tiles; tot->span_samples = span;
   tot->out_floats = (out_mode == B200FEAT_OUT_PADDED ? (int64_t)B * tmax : rows) * h->plan.F;
+  if (h->plan.whisper) tot->out_floats += B;  // scratch tail: per-cut maxima
   return B200FEAT_OK;
 }
 
@@ -379,7 +395,7 @@ int b200feat_plan_batch(const b200feat_handle *hc, const int64_t *num_samples,
 static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt, const int64_t *meta_dev,
                         int32_t B, int32_t b0, int32_t b1, int64_t tile0, int64_t tile1,
                         int64_t max_frames, float *out_dev, int32_t out_mode, float pad_value,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, float *cut_max_dev = nullptr, int64_t norm_rows = 0) {
   DevBatch db;
   db.samples = samples_dev;
   db.samp_off = meta_dev + b0;
@@ -388,6 +404,7 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   db.tile_off = meta_dev + 3 * (int64_t)B + 1 + b0;
   db.tile_cut = h->frames_per_tile > 1 ? reinterpret_cast<const int32_t *>(meta_dev + 4 * (int64_t)B + 2) : nullptr;
   db.out = out_dev;
+  db.cut_max = cut_max_dev ? cut_max_dev + b0 : nullptr;
   db.tile_base = tile0;
   db.num_tiles = tile1 - tile0;
   db.max_frames = max_frames;
@@ -396,6 +413,11 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   db.out_mode = out_mode;
   db.pad_value = pad_value;
   if (db.num_tiles <= 0) return 0;
+  if (h->plan.whisper) {
+    if (!cut_max_dev) return fail(h, B200FEAT_EINVAL, "whisper-fbank: scratch missing");
+    cudaError_t e = cudaMemsetAsync(db.cut_max, 0xff, (size_t)db.B * sizeof(float), stream);  // "empty" (common.cuh)
+    if (e != cudaSuccess) return fail(h, B200FEAT_ECUDA, std::string("memset(cut_max): ") + cudaGetErrorString(e));
+  }
   if (h->kernel == B200FEAT_KERNEL_FAST_X2) {
     int rc = fastx2_launch(h->plan, h->fastx2, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512x2 launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -423,6 +445,14 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, B200FEAT_ECUDA, std::string("generic launch: ") + cudaGetErrorString(e));
   }
+  if (h->plan.whisper && norm_rows > 0) {  // second launch: clamp to the cut's maximum - 8, (x + 4) / 4, zero rows
+    int64_t blocks = (norm_rows + 7) / 8;
+    const int64_t cap = (int64_t)h->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    b200feat_whisper_normalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h->plan, db, norm_rows);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, B200FEAT_ECUDA, std::string("whisper normalise launch: ") + cudaGetErrorString(e));
+  }
   return 0;
 }
 
@@ -434,14 +464,16 @@ int b200feat_extract(b200feat_handle *h, const void *samples_dev, int32_t dt, co
   int prev = 0;
   cudaGetDevice(&prev);
   if (prev != h->device) cudaSetDevice(h->device);
+  const int64_t all_rows = out_mode == B200FEAT_OUT_PADDED ? (int64_t)B * tot->max_frames : tot->total_rows;
+  float *scratch = h->plan.whisper ? out_dev + all_rows * h->plan.F : nullptr;
   int rc = launch_range(h, samples_dev, dt, meta_dev, B, 0, B, 0, tot->total_tiles, tot->max_frames, out_dev,
-                        out_mode, pad_value, (cudaStream_t)stream);
+                        out_mode, pad_value, (cudaStream_t)stream, scratch, all_rows);
   if (prev != h->device) cudaSetDevice(prev);
   if (rc) return rc;
   {
     std::lock_guard<std::mutex> g(h->stats_mu);
     h->stats.calls++; h->stats.cuts += B; h->stats.frames += tot->total_rows;
-    h->stats.kernel_launches++;
+    h->stats.kernel_launches += h->plan.whisper ? 2 : 1;
   }
   return B200FEAT_OK;
 }
@@ -496,6 +528,7 @@ int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t 
   // H2D(i+1), kernel(i) and D2H(i-1) overlap (PCIe is the end-to-end bound)
   const int64_t *soff = r.h_meta, *roff = r.h_meta + 2 * (int64_t)B, *toff = r.h_meta + 3 * (int64_t)B + 1;
   const int64_t chunk_elems = (32ll << 20) / (int64_t)esz;
+  float *scratch = h->plan.whisper ? r.d_out + (tot.out_floats - B) : nullptr;
   int b0 = 0, ci = 0, launches = 0;
   while (b0 < B) {
     int b1 = b0 + 1;
@@ -505,13 +538,13 @@ int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t 
     const int64_t e0 = soff[b0], e1 = soff[b1 - 1] + num_samples[b1 - 1];
     CU_TRY(h, cudaMemcpyAsync((char *)r.d_samples + e0 * esz, (const char *)samples_host + e0 * esz,
                               (size_t)(e1 - e0) * esz, cudaMemcpyHostToDevice, st));
-    rc = launch_range(h, r.d_samples, dt, r.d_meta, B, b0, b1, toff[b0], toff[b1], tot.max_frames, r.d_out,
-                      out_mode, pad_value, st);
-    if (rc) return rc;
-    ++launches;
     int64_t f0, f1;
     if (out_mode == B200FEAT_OUT_PADDED) { f0 = (int64_t)b0 * tot.max_frames; f1 = (int64_t)b1 * tot.max_frames; }
     else { f0 = roff[b0]; f1 = roff[b1]; }
+    rc = launch_range(h, r.d_samples, dt, r.d_meta, B, b0, b1, toff[b0], toff[b1], tot.max_frames, r.d_out,
+                      out_mode, pad_value, st, scratch, f1 - f0);
+    if (rc) return rc;
+    launches += h->plan.whisper ? 2 : 1;
     CU_TRY(h, cudaMemcpyAsync(out_host + f0 * h->plan.F, r.d_out + f0 * h->plan.F,
                               (size_t)(f1 - f0) * h->plan.F * 4, cudaMemcpyDeviceToHost, st));
     b0 = b1; ++ci;

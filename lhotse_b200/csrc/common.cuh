@@ -15,7 +15,9 @@ struct DevPlan {
   int feature, L, S, N, K, M, C, F;  // F = output row width
   int Nc;                            // complex FFT length: N/2 (even N, packed real) or N (odd N)
   int packed;                        // 1 if even N
-  int pad_left;                      // (L - S) / 2 when !snip_edges
+  int pad_left;                      // (L - S) / 2 when !snip_edges (B200FEAT_PAD_KALDI); N / 2 with B200FEAT_PAD_CENTER
+  int pad_mode;                      // B200FEAT_PAD_*: 0 mirrors with the edge sample, 1 without (torch "reflect")
+  int whisper;                       // feature == B200FEAT_WHISPER_FBANK: log10 epilogue + per-cut max, n / S valid frames
   int snip_edges, remove_dc, use_energy, raw_energy, use_mag, energy_style, use_lifter;
   int nstages;
   int radix[B200_MAX_STAGES];
@@ -40,6 +42,7 @@ struct DevBatch {
   const int64_t *tile_off;  // [B+1] tile prefix (absolute)
   const int32_t *tile_cut;  // [total tiles] absolute tile -> absolute cut (tiled kernels), or nullptr
   float *out;
+  float *cut_max;       // [B] per-cut running maximum (whisper-fbank only; bit pattern 0xffffffff = empty)
   int64_t tile_base;    // first tile of this launch (absolute)
   int64_t num_tiles;    // tiles in this launch
   int64_t max_frames;   // T_max (padded mode)
@@ -64,11 +67,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// index of the sample feeding (frame t, tap j): layers.py:753-772 in closed form
-__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n) {
-  if (i < 0) i = -i - 1;
-  if (i >= n) i = 2 * n - 1 - i;
+// index of the sample feeding (frame t, tap j): layers.py:753-772 in closed form (mode 0: the mirror repeats the edge
+// sample); mode 1 is torch's "reflect" padding of torch.stft(center=True) (whisper_fbank.py:62): the edge is not repeated
+__device__ __forceinline__ int64_t reflect_index(int64_t i, int64_t n, int mode = 0) {
+  if (i < 0) i = -i - 1 + mode;
+  if (i >= n) i = 2 * n - 1 - mode - i;
   return i;
+}
+
+// running float maximum in global memory with torch.max semantics (NaN wins): non-negative floats order like signed
+// ints, negative floats like reversed unsigned ints; the slot starts as 0xffffffff (cudaMemset 0xff), which loses to
+// every real value on both branches; the canonical NaN 0x7fffffff wins both
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  if (v != v) v = __int_as_float(0x7fffffff);
+  if (__float_as_int(v) >= 0) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));
 }
 
 // largest b in [0, B) with prefix[b] <= g   (prefix has B+1 entries, prefix[0] <= g < prefix[B])
@@ -90,11 +103,12 @@ __device__ __forceinline__ float nanmax(float x, float floor_) {
 
 // log(x) for x known to be a normal float (the mel floor keeps it >= 1.19e-7): MUFU.LG2 * ln 2, i.e. __logf without its
 // denormal-input fix-up (8 extra instructions per value); NaN and +inf pass through
-__device__ __forceinline__ float fast_log_normal(float x) {
+__device__ __forceinline__ float fast_lg2_normal(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r * 0.69314718055994530942f;
+  return r;
 }
+__device__ __forceinline__ float fast_log_normal(float x) { return fast_lg2_normal(x) * 0.69314718055994530942f; }
 
 __device__ __forceinline__ float log_energy_value(const DevPlan &p, float e) {
   float le;

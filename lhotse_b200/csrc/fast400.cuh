@@ -154,6 +154,8 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
     const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED ? (int64_t)(b.batch_first + cut) * b.max_frames + t0
                                                            : __ldg(b.row_off + cut) + t0;
     const int nvalid = (int)max((int64_t)0, min((int64_t)F400_SLOTS, T - t0));
+    // whisper-fbank: only the stft's n / S frames feed the cut-wide maximum (whisper_fbank.py:63-68)
+    const int nmaxed = p.whisper ? (int)max((int64_t)0, min((int64_t)F400_SLOTS, n / p.S - t0)) : 0;
     float le[F400_SLOTS];
 #pragma unroll
     for (int k = 0; k < F400_SLOTS; ++k) le[k] = 0.f;
@@ -189,7 +191,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
 #pragma unroll 5
         for (int i = 0; i < 25; ++i) {
           int64_t ia = base + 16 * i + 2 * l, ib = ia + 1;
-          if (!p.snip_edges) { ia = reflect_index(ia, n); ib = reflect_index(ib, n); }
+          if (!p.snip_edges) { ia = reflect_index(ia, n, p.pad_mode); ib = reflect_index(ib, n, p.pad_mode); }
           const float2 x = make_float2(ld_sample<DT>(b.samples, xoff + ia), ld_sample<DT>(b.samples, xoff + ib));
           *reinterpret_cast<float2 *>(S + 16 * i + 2 * l) = x;
           s += x.x + x.y;
@@ -294,6 +296,8 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(X);  // the exchange tile is idle during the epilogue
+      const float lgk = p.whisper ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (whisper_fbank.py:67) or ln
+      float vmax = __int_as_float(0xff800000);
       // rounds of 16 filters, two per lane (l and l + 8): the per-round overhead is shared by 2 filters x 2 frames
       for (int j = 0; j < ft.mel_rounds; ++j) {
         const int4 ra = s_rdesc[j * 16 + l], rb = s_rdesc[j * 16 + l + 8];
@@ -318,8 +322,11 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
           if (m < p.M) {
             float r[F400_SLOTS];
 #pragma unroll
-            for (int f = 0; f < F400_SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[h][f], p.mel_floor));
-            if (p.feature == B200FEAT_FBANK) {
+            for (int f = 0; f < F400_SLOTS; ++f) {
+              r[f] = fast_lg2_normal(nanmax(acc[h][f], p.mel_floor)) * lgk;
+              if (f < nmaxed) vmax = nanmax(vmax, r[f]);
+            }
+            if (p.feature != B200FEAT_MFCC) {
               float *orow = out + m + shift;
 #pragma unroll
               for (int f = 0; f < F400_SLOTS; ++f)
@@ -331,7 +338,11 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
           }
         }
       }
-      if (p.feature == B200FEAT_FBANK) {
+      if (p.whisper) {  // one atomic per warp: its four quarter-warps work on the same cut
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = nanmax(vmax, __shfl_xor_sync(F512_FULL, vmax, o));
+        if ((tid & 31) == 0 && vmax != __int_as_float(0xff800000)) atomic_max_float(b.cut_max + cut, vmax);
+      } else if (p.feature == B200FEAT_FBANK) {
         if (shift && l < nvalid) {
           float v0 = 0.f;
 #pragma unroll

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
     float s = 0.f;
     for (int j = lane; j < p.L; j += 32) {
       int64_t i = base + j;
-      if (!p.snip_edges) i = reflect_index(i, n);
+      if (!p.snip_edges) i = reflect_index(i, n, p.pad_mode);
       const float v = ld_sample<DT>(b.samples, xoff + i);
       raw[j] = v;
       s += v;
@@ -188,15 +188,24 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
     } else {
       float *mlog = reinterpret_cast<float *>(dst);  // scratch (FFT buffer not holding the result)
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      float vmax = __int_as_float(0xff800000);  // -inf
       for (int m = lane; m < p.M; m += 32) {
         const int st = __ldg(p.mel_start + m), len = __ldg(p.mel_len + m);
         const float *w = p.mel_w + __ldg(p.mel_woff + m);
         float acc = 0.f;
         for (int i = 0; i < len; ++i) acc += raw[st + i] * __ldg(w + i);
-        const float v = logf(nanmax(acc, p.mel_floor));
-        if (p.feature == B200FEAT_FBANK) out[m + shift] = v; else mlog[m] = v;
+        const float fl = nanmax(acc, p.mel_floor);
+        const float v = p.whisper ? log10f(fl) : logf(fl);  // whisper_fbank.py:67
+        vmax = nanmax(vmax, v);
+        if (p.feature == B200FEAT_MFCC) mlog[m] = v; else out[m + shift] = v;
       }
-      if (p.feature == B200FEAT_FBANK) {
+      if (p.whisper) {
+        // the cut-wide maximum the normalise pass clamps against (whisper_fbank.py:68); rows past the stft's n / S
+        // frames exist only as zero rows (:73-80) and do not take part
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = nanmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if (lane == 0 && t < n / p.S) atomic_max_float(b.cut_max + cut, vmax);
+      } else if (p.feature == B200FEAT_FBANK) {
         if (shift && lane == 0) out[0] = le;
       } else {
         __syncwarp();
@@ -210,5 +219,37 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
       }
     }
     __syncwarp();
+  }
+}
+
+
+// Second launch of the whisper-fbank path (whisper_fbank.py:68-80): x -> (max(x, cut_max - 8) + 4) / 4 for the rows the
+// stft produced (t < n / S), 0 for the extra row `compute_num_frames_from_samples` asks for; padded rows keep pad_value.
+// One warp per output row; reads and writes 4*F bytes per row.
+__global__ void __launch_bounds__(256) b200feat_whisper_normalize_kernel(const DevPlan p, const DevBatch b, int64_t nrows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t first_row = __ldg(b.row_off);
+  for (int64_t g = warp; g < nrows; g += nwarps) {
+    int cut;
+    int64_t t, out_row;
+    if (b.out_mode == B200FEAT_OUT_PADDED) {
+      cut = (int)(g / b.max_frames);
+      t = g - (int64_t)cut * b.max_frames;
+      out_row = (int64_t)(b.batch_first + cut) * b.max_frames + t;
+      if (t >= __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut)) continue;  // pad row: already pad_value
+    } else {
+      out_row = first_row + g;
+      cut = find_segment(b.row_off, b.B, out_row);
+      t = out_row - __ldg(b.row_off + cut);
+    }
+    float *o = b.out + out_row * p.F;
+    if (t >= __ldg(b.nsamp + cut) / p.S) {
+      for (int c = lane; c < p.F; c += 32) o[c] = 0.f;
+    } else {
+      const float thr = b.cut_max[cut] - 8.0f;
+      for (int c = lane; c < p.F; c += 32) o[c] = (nanmax(o[c], thr) + 4.0f) * 0.25f;
+    }
   }
 }

@@ -41,7 +41,7 @@ class PlanDesc(C.Structure):
         ("num_ceps", C.c_int32), ("snip_edges", C.c_int32), ("remove_dc_offset", C.c_int32),
         ("use_energy", C.c_int32), ("raw_energy", C.c_int32), ("use_fft_mag", C.c_int32),
         ("energy_style", C.c_int32), ("use_lifter", C.c_int32), ("kernel", C.c_int32),
-        ("reserved0", C.c_int32), ("preemph_coeff", C.c_float), ("energy_floor", C.c_float),
+        ("pad_mode", C.c_int32), ("preemph_coeff", C.c_float), ("energy_floor", C.c_float),
         ("mel_floor", C.c_float), ("log_spec_eps", C.c_float),
     ]
 
@@ -144,6 +144,7 @@ class Engine:
         d.energy_style = plan.energy_style
         d.use_lifter = int(plan.lifter is not None)
         d.kernel = KERNELS[kernel]
+        d.pad_mode = int(getattr(plan, "pad_mode", 0))
         d.preemph_coeff, d.energy_floor = plan.preemph_coeff, plan.energy_floor
         d.mel_floor, d.log_spec_eps = plan.mel_floor, plan.log_spec_eps
         tabs = [None if t is None else np.ascontiguousarray(t, dtype=np.float32)
@@ -218,14 +219,18 @@ class Engine:
             row_prefix = meta[2 * B: 3 * B + 1]
         else:
             row_prefix = None
+        shape = (B, totals.max_frames, self.feature_dim) if out_mode == OUT_PADDED else (totals.total_rows, self.feature_dim)
         if out is None:
-            shape = (B, totals.max_frames, self.feature_dim) if out_mode == OUT_PADDED else (totals.total_rows, self.feature_dim)
-            out = torch.empty(shape, dtype=torch.float32, device=samples.device)
+            # one flat allocation of totals.out_floats: the feature rows, then (whisper-fbank) the library's scratch tail
+            flat = torch.empty(int(totals.out_floats), dtype=torch.float32, device=samples.device)
         else:
             assert out.is_cuda and out.is_contiguous() and out.numel() >= totals.out_floats
+            flat = out.view(-1)
         stream = torch.cuda.current_stream(samples.device).cuda_stream
         self._check(self.lib.b200feat_extract(self._h, samples.data_ptr(), dt, meta_dev.data_ptr(), B,
-                                              C.byref(totals), out.data_ptr(), out_mode, float(pad_value), stream))
+                                              C.byref(totals), flat.data_ptr(), out_mode, float(pad_value), stream))
+        if out is None:
+            out = flat[: shape[0] * shape[1] * (shape[2] if len(shape) == 3 else 1)].view(shape)
         return out, row_prefix
 
     # ------------------------------------------------------------------ host-to-host path
@@ -246,7 +251,7 @@ class Engine:
         assert int(ns.sum()) <= numel
         B = len(ns)
         p = self.plan
-        if p.snip_edges:
+        if p.snip_edges and p.feature != "whisper-fbank":
             Ts = np.where(ns < p.L, 0, 1 + (ns - p.L) // p.S)
         else:
             Ts = (ns + p.S // 2) // p.S

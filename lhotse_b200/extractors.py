@@ -8,6 +8,7 @@ B200-native counterparts of lhotse's Kaldi-family extractors, behind the unchang
     Mfcc            :201  name "kaldi-mfcc"                    B200Mfcc            "b200-mfcc"
     Spectrogram     :297  name "kaldi-spectrogram"             B200Spectrogram     "b200-spectrogram"
     LogSpectrogram  :407  name "kaldi-log-spectrogram"         B200LogSpectrogram  "b200-log-spectrogram"
+    WhisperFbank (lhotse/features/whisper_fbank.py:103)  "whisper-fbank"    B200WhisperFbank    "b200-whisper-fbank"
 
 Same config fields, same container rules for ``extract`` / ``extract_batch``
 (extractors.py:92-132, :485-554), same ``mix`` / ``compute_energy`` / ``scale`` statics.
@@ -459,9 +460,64 @@ class B200LogSpectrogram(B200Spectrogram):
     feature_kind = "log-spectrogram"
 
 
+@dataclass
+class B200WhisperFbankConfig:
+    """WhisperFbankConfig (whisper_fbank.py:87-98: `num_filters`, `device`) plus the `kernel` knob.  The geometry is
+    fixed by the reference's constructor (:107-111): 16 kHz, n_fft 400, hop 160 — class constants here, so that
+    `to_dict()` stays loadable by the reference's config class once `kernel` is dropped."""
+
+    num_filters: int = 80
+    device: str = "cuda"
+    kernel: str = "auto"  # auto | fast (N = 400 prime-factor kernel) | generic
+
+    sampling_rate = 16000   # not dataclass fields: constants of the extractor
+    frame_shift = 0.01
+    frame_length = 0.025
+    dither = 0.0
+    snip_edges = False
+
+    def to_dict(self) -> Dict[str, Any]:
+        return _asdict_nonull(self)
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any]):
+        return cls(**data)
+
+
+@register_extractor
+class B200WhisperFbank(_B200Extractor):
+    """`WhisperFbank` (whisper_fbank.py:103-184) on the fused N = 400 kernel: torch.stft(center=True) framing, periodic
+    Hann window, |X|^2, librosa/Slaney mel filters, log10, clamp to the cut's maximum - 8, (x + 4) / 4, one zero row when
+    `compute_num_frames_from_samples` asks for one more frame than the stft yields (:73-80).  The per-cut maximum makes it
+    two launches per batch (fused kernel with an atomic per-cut max, then a 640 B/row normalise pass).
+    In a batch every cut is normalised by its OWN maximum, i.e. `extract_batch(xs)[i] == extract(xs[i])` — what the
+    reference's default `extract_batch` (base.py:152-222, a loop over `extract`) produces for unpadded inputs."""
+
+    name = "b200-whisper-fbank"
+    config_type = B200WhisperFbankConfig
+    feature_kind = "whisper-fbank"
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self.config.num_filters
+
+    def extract(self, samples: ArrayLike, sampling_rate: int) -> ArrayLike:
+        if samples.ndim == 2 and samples.shape[0] > 1:  # whisper_fbank.py:54-56
+            raise ValueError("Whisper Fbank works only with single-channel recordings.")
+        return super().extract(samples, sampling_rate)
+
+    def online_inference(self, samples, context=None):
+        raise NotImplementedError("WhisperFbank has no streaming mode (its normalisation needs the whole utterance)")
+
+    # same statics as the reference class (whisper_fbank.py:167-184)
+    mix = staticmethod(B200Fbank.mix)
+    compute_energy = staticmethod(B200Fbank.compute_energy)
+    scale = staticmethod(B200Fbank.scale)
+
+
 _ALIASES = {
     "kaldi-fbank": B200Fbank, "kaldi-mfcc": B200Mfcc,
     "kaldi-spectrogram": B200Spectrogram, "kaldi-log-spectrogram": B200LogSpectrogram,
+    "whisper-fbank": B200WhisperFbank,
 }
 
 

@@ -20,8 +20,9 @@ import torch
 EPSILON = 1e-10  # lhotse/utils.py:50
 LOG_EPSILON = math.log(EPSILON)  # lhotse/utils.py:51 — the collation pad value
 
-FEATURE_KINDS = {"fbank": 0, "mfcc": 1, "spectrogram": 2, "log-spectrogram": 3}
+FEATURE_KINDS = {"fbank": 0, "mfcc": 1, "spectrogram": 2, "log-spectrogram": 3, "whisper-fbank": 4}
 ENERGY_LHOTSE, ENERGY_KALDI = 0, 1
+PAD_KALDI, PAD_CENTER = 0, 1  # include/b200feat.h B200FEAT_PAD_*
 WINDOWS = ("hamming", "hanning", "povey", "rectangular", "blackman")
 
 
@@ -111,6 +112,47 @@ def make_mel_bank(
     return np.ascontiguousarray(B.astype(np.float32))
 
 
+def _slaney_hz_to_mel(f):
+    f = np.asanyarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-30) / min_log_hz) / logstep, f / f_sp)
+
+
+def _slaney_mel_to_hz(m):
+    m = np.asanyarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz = 1000.0
+    min_log_mel = min_log_hz / f_sp
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def make_slaney_mel_bank(sampling_rate: int, n_fft: int, n_mels: int, fmin: float = 0.0,
+                         fmax: Optional[float] = None) -> np.ndarray:
+    """Dense (K = n_fft//2 + 1, M) float32 bank = ``librosa.filters.mel(sr, n_fft, n_mels).T`` — what WhisperFbank
+    builds at whisper_fbank.py:117-120 (librosa defaults: Slaney mel scale, htk=False, norm="slaney", float32 output).
+    librosa is a third-party dependency that is absent from the reference tree and from this image; this restates its
+    published algorithm (librosa/filters.py ``mel``: triangles in Hz between Slaney-mel-spaced corner frequencies, each
+    scaled by 2 / (f[m+2] - f[m]), evaluated in float64 and cast to float32).  tests/test_whisper.py pins it bit-for-bit
+    to transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney"), which upstream tests against librosa."""
+    fmax = sampling_rate / 2 if fmax is None else fmax
+    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sampling_rate)
+    mel_f = _slaney_mel_to_hz(np.linspace(_slaney_hz_to_mel(fmin), _slaney_hz_to_mel(fmax), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = np.subtract.outer(mel_f, fftfreqs)
+    w = np.zeros((n_mels, 1 + n_fft // 2), dtype=np.float64)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        w[i] = np.maximum(0, np.minimum(lower, upper))
+    enorm = 2.0 / (mel_f[2 : n_mels + 2] - mel_f[:n_mels])
+    w *= enorm[:, np.newaxis]
+    return np.ascontiguousarray(w.astype(np.float32).T)
+
+
 def make_dct(num_ceps: int, num_filters: int) -> np.ndarray:
     n = torch.arange(float(num_filters)).unsqueeze(1)
     k = torch.arange(float(num_ceps))
@@ -147,6 +189,7 @@ class FeaturePlan:
     mel_floor: float = float(torch.finfo(torch.float).eps)  # layers.py:533-535
     log_spec_eps: float = 1e-15  # layers.py:467
     dither: float = 0.0
+    pad_mode: int = PAD_KALDI
     window: np.ndarray = field(default=None, repr=False)
     mel_bank: Optional[np.ndarray] = field(default=None, repr=False)
     dct: Optional[np.ndarray] = field(default=None, repr=False)
@@ -160,13 +203,15 @@ class FeaturePlan:
     def feature_dim(self) -> int:
         if self.feature == "fbank":
             return self.num_filters + (1 if self.use_energy else 0)
+        if self.feature == "whisper-fbank":
+            return self.num_filters
         if self.feature == "mfcc":
             return self.num_ceps
         return self.K
 
     def num_frames(self, n: int) -> int:
-        """layers.py:747-753 (the in-layer twin of utils.py:424-434)."""
-        if self.snip_edges:
+        """layers.py:747-753 (the in-layer twin of utils.py:424-434); whisper-fbank: whisper_fbank.py:73-80."""
+        if self.snip_edges and self.feature != "whisper-fbank":
             return 0 if n < self.L else 1 + (n - self.L) // self.S
         return (n + self.S // 2) // self.S
 
@@ -207,6 +252,8 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
     KaldifeatFbankConfig/KaldifeatMfccConfig (kaldifeat.py:149-175, :218-246), duck-typed by field names."""
     if feature not in FEATURE_KINDS:
         raise ValueError(f"unknown feature kind {feature}")
+    if feature == "whisper-fbank":
+        return build_whisper_plan(cfg)
     frame = _get(cfg, "frame_opts", default=cfg)  # kaldifeat nests the frame options
     melo = _get(cfg, "mel_opts", default=cfg)
     compat = getattr(cfg, "compat", "lhotse")  # our configs carry the family explicitly
@@ -274,4 +321,23 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
         plan.num_ceps = C
         plan.dct = make_dct(C, plan.num_filters)
         plan.lifter = make_lifter(C, float(_get(cfg, "cepstral_lifter", default=22)))
+    return plan
+
+
+def build_whisper_plan(cfg: Any) -> FeaturePlan:
+    """WhisperFbankConfig (whisper_fbank.py:87-98: `num_filters`, `device`) -> plan.  Everything else is fixed by the
+    reference's constructor (whisper_fbank.py:107-123): 16 kHz, n_fft = 400, hop 160, periodic Hann window, librosa
+    (Slaney) mel filters over 0..8000 Hz; log_mel_spectrogram (:16-84): torch.stft(center=True) framing without DC
+    removal or pre-emphasis, |X|^2, mel, log10(max(., 1e-10)), clamp to the utterance maximum - 8, (x + 4) / 4."""
+    M = int(_get(cfg, "num_filters", default=80))
+    if M < 1:
+        raise ValueError("num_filters must be positive")
+    sr, n_fft, hop = 16000, 400, 160
+    plan = FeaturePlan(
+        feature="whisper-fbank", sampling_rate=sr, L=n_fft, S=hop, N=n_fft, num_filters=M,
+        snip_edges=False, remove_dc_offset=False, use_energy=False, raw_energy=True, use_fft_mag=False,
+        preemph_coeff=0.0, mel_floor=1e-10, pad_mode=PAD_CENTER,
+    )
+    plan.window = torch.hann_window(n_fft).to(torch.float32).numpy().copy()  # whisper_fbank.py:116 (periodic)
+    plan.mel_bank = make_slaney_mel_bank(sr, n_fft, M)
     return plan

@@ -28,10 +28,38 @@ def import_reference():
             try:
                 __import__(m)
             except Exception:
-                sys.modules[m] = _Stub(m)
+                import importlib.machinery
+
+                stub = _Stub(m)
+                stub.__spec__ = importlib.machinery.ModuleSpec(m, None)  # keeps importlib.util.find_spec(m) working
+                sys.modules[m] = stub
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     sys.dont_write_bytecode = True
     import lhotse  # noqa
 
     return lhotse
+
+
+def install_librosa_standin():
+    """`WhisperFbank` takes its mel table from `librosa.filters.mel` (whisper_fbank.py:117-120) and refuses to construct
+    without librosa (:112-115).  librosa is not in this image: register a stand-in whose `filters.mel` is the table of
+    `transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")` — an independent third-party
+    implementation that upstream tests against librosa.  Raises ImportError when transformers is missing."""
+    import importlib.machinery
+
+    import numpy as np
+    from transformers.audio_utils import mel_filter_bank
+
+    if "librosa" in sys.modules and not getattr(sys.modules["librosa"], "_b200_standin", False):
+        return  # the real thing
+    def mel(sr, n_fft, n_mels):
+        return mel_filter_bank(1 + n_fft // 2, n_mels, 0.0, sr / 2, sr, norm="slaney", mel_scale="slaney").T.astype(np.float32)
+
+    lib = types.ModuleType("librosa")
+    lib.__spec__ = importlib.machinery.ModuleSpec("librosa", None)
+    lib._b200_standin = True
+    lib.filters = types.ModuleType("librosa.filters")
+    lib.filters.mel = mel
+    sys.modules["librosa"] = lib
+    sys.modules["librosa.filters"] = lib.filters
