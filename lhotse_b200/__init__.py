@@ -15,6 +15,18 @@ from .extractors import (  # noqa: F401
     from_reference_config,
     install_as_default,
 )
+from .families import (  # noqa: F401
+    B200KaldifeatFbank,
+    B200KaldifeatFbankConfig,
+    B200KaldifeatFrameOptions,
+    B200KaldifeatMelOptions,
+    B200KaldifeatMfcc,
+    B200KaldifeatMfccConfig,
+    B200TorchaudioFbank,
+    B200TorchaudioFbankConfig,
+    B200TorchaudioMfcc,
+    B200TorchaudioMfccConfig,
+)
 from .engine import Engine, B200FeatError, load_library  # noqa: F401
 
 __version__ = "0.1.0"

@@ -527,8 +527,9 @@ def install_as_default() -> None:
     `create_default_feature_extractor`, base.py:381, used by MixedCut.load_features mixed.py:1252)
     pick the GPU implementation without editing them."""
     from .base import _REGISTRY
+    from .families import FAMILY_ALIASES  # "fbank" / "mfcc" (torchaudio family), "kaldifeat-fbank" / "kaldifeat-mfcc"
 
-    for name, cls in _ALIASES.items():
+    for name, cls in {**_ALIASES, **FAMILY_ALIASES}.items():
         _REGISTRY[name] = cls
 
 
