@@ -195,6 +195,15 @@ int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t 
                           const int64_t *num_samples, int32_t batch, float *out_host,
                           int32_t out_mode, float pad_value);
 
+/*
+ * Same, with the cuts at caller-chosen element offsets inside `samples_host` (increasing, non-overlapping; NULL = back to
+ * back as above).  Starting every cut on an even element keeps the kernels on their vector-load path: with back-to-back
+ * staging every cut that follows an odd-length one is fetched tap by tap (correct, slower).
+ */
+int b200feat_extract_host_at(b200feat_handle *h, const void *samples_host, int32_t sample_dtype,
+                             const int64_t *num_samples, const int64_t *sample_offsets, int32_t batch,
+                             float *out_host, int32_t out_mode, float pad_value);
+
 /* Read back a device-resident constant table (tests / NCCL-broadcast verification).
  * which: 0 window, 1 dense mel bank reconstructed from the sparse form (K x M), 2 dct, 3 lifter,
  * 4 twiddles (interleaved re,im). Returns the number of floats written or a negative code. */

@@ -481,7 +481,20 @@ int b200feat_extract(b200feat_handle *h, const void *samples_dev, int32_t dt, co
 int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t dt,
                           const int64_t *num_samples, int32_t B, float *out_host, int32_t out_mode,
                           float pad_value) {
+  return b200feat_extract_host_at(h, samples_host, dt, num_samples, nullptr, B, out_host, out_mode, pad_value);
+}
+
+int b200feat_extract_host_at(b200feat_handle *h, const void *samples_host, int32_t dt,
+                             const int64_t *num_samples, const int64_t *sample_offsets, int32_t B,
+                             float *out_host, int32_t out_mode, float pad_value) {
   if (!h || !samples_host || !num_samples || !out_host || B <= 0) return fail(h, B200FEAT_EINVAL, "extract_host: bad arguments");
+  if (sample_offsets) {
+    int64_t end = 0;
+    for (int i = 0; i < B; ++i) {
+      if (sample_offsets[i] < end) return fail(h, B200FEAT_EINVAL, "extract_host_at: offsets must be increasing and non-overlapping");
+      end = sample_offsets[i] + num_samples[i];
+    }
+  }
   if (dt != B200FEAT_F32 && dt != B200FEAT_I16) return fail(h, B200FEAT_EINVAL, "bad sample dtype");
   HostRing &r = h->ring;
   std::lock_guard<std::mutex> guard(r.mu);
@@ -500,8 +513,8 @@ int b200feat_extract_host(b200feat_handle *h, const void *samples_host, int32_t 
     r.h_meta_cap = (size_t)words;
   }
   b200feat_batch_totals tot;
-  // host layout is back-to-back (align 1) so the user's buffer is copied verbatim
-  int rc = b200feat_plan_batch(h, num_samples, nullptr, B, 1, out_mode, r.h_meta, words, &tot);
+  // the host layout (back to back unless the caller supplied offsets) is kept on the device: chunks are copied verbatim
+  int rc = b200feat_plan_batch(h, num_samples, sample_offsets, B, 1, out_mode, r.h_meta, words, &tot);
   if (rc) return rc;
   for (auto &s : r.streams) if (!s) CU_TRY(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   if (!r.meta_ready) CU_TRY(h, cudaEventCreateWithFlags(&r.meta_ready, cudaEventDisableTiming));

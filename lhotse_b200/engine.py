@@ -60,6 +60,7 @@ EXPORTS = [
     "b200feat_version", "b200feat_global_error", "b200feat_create", "b200feat_destroy",
     "b200feat_last_error", "b200feat_num_frames", "b200feat_feature_dim", "b200feat_kernel_kind",
     "b200feat_meta_words", "b200feat_plan_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
+    "b200feat_extract_host_at",
     "b200feat_get_table", "b200feat_get_stats",
 ]
 
@@ -108,6 +109,8 @@ def load_library():
         lib.b200feat_extract.argtypes = [vp, vp, i32, vp, i32, C.POINTER(BatchTotals), vp, i32, C.c_float, vp]
         lib.b200feat_extract_host.restype = C.c_int
         lib.b200feat_extract_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.c_float]
+        lib.b200feat_extract_host_at.restype = C.c_int
+        lib.b200feat_extract_host_at.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, C.c_float]
         lib.b200feat_get_table.restype = i64
         lib.b200feat_get_table.argtypes = [vp, i32, vp, i64]
         lib.b200feat_get_stats.restype = C.c_int
@@ -236,9 +239,11 @@ class Engine:
     # ------------------------------------------------------------------ host-to-host path
     def extract_host(self, samples: Union[np.ndarray, torch.Tensor], num_samples: Sequence[int],
                      out_mode: int = OUT_PACKED, pad_value: float = 0.0,
-                     out: Optional[Union[np.ndarray, torch.Tensor]] = None):
-        """samples: the cuts back to back in ONE host buffer (numpy or CPU torch tensor, float32 or
-        int16; pinned memory makes the H2D copies asynchronous).  Blocks until `out` is filled."""
+                     out: Optional[Union[np.ndarray, torch.Tensor]] = None,
+                     offsets: Optional[Sequence[int]] = None):
+        """samples: the cuts in ONE host buffer (numpy or CPU torch tensor, float32 or int16; pinned memory makes the
+        H2D copies asynchronous), back to back or at the increasing element `offsets` (`stage_host` aligns them so
+        that the kernels stay on their vector-load path).  Blocks until `out` is filled."""
         if isinstance(samples, torch.Tensor):
             assert not samples.is_cuda and samples.is_contiguous()
             dt = {torch.float32: DT_F32, torch.int16: DT_I16}[samples.dtype]
@@ -248,7 +253,8 @@ class Engine:
             dt = {np.dtype(np.float32): DT_F32, np.dtype(np.int16): DT_I16}[samples.dtype]
             sptr, numel = samples.ctypes.data, samples.size
         ns = np.ascontiguousarray(num_samples, dtype=np.int64)
-        assert int(ns.sum()) <= numel
+        off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int64)
+        assert (int(ns.sum()) if off is None else int(off[-1] + ns[-1])) <= numel
         B = len(ns)
         p = self.plan
         if p.snip_edges and p.feature != "whisper-fbank":
@@ -263,7 +269,7 @@ class Engine:
             # host allocator makes repeated allocations of the same size cheap
             out = torch.empty(shape, dtype=torch.float32, pin_memory=True).numpy()
         optr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
-        rc = self.lib.b200feat_extract_host(self._h, sptr, dt, _ptr(ns), B, optr, out_mode, float(pad_value))
+        rc = self.lib.b200feat_extract_host_at(self._h, sptr, dt, _ptr(ns), _ptr(off), B, optr, out_mode, float(pad_value))
         if rc == -5:
             raise ValueError(self.lib.b200feat_last_error(self._h).decode())
         self._check(rc)
@@ -305,3 +311,23 @@ def pack_device(tensors: List[torch.Tensor], device: torch.device, align: int = 
     for t, o, n in zip(tensors, offs, lens):
         buf[o:o + n].copy_(t.reshape(-1), non_blocking=True)
     return buf, lens, offs
+
+
+def stage_host(arrays: Sequence[np.ndarray], dtype=np.float32, align: int = 4) -> Tuple[torch.Tensor, List[int], List[int]]:
+    """Copies 1-D host waveforms into ONE pinned buffer, each start aligned to `align` elements (gaps are zero-filled so
+    that no uninitialised memory crosses PCIe).  Returns (buffer, lengths, offsets) for `Engine.extract_host(offsets=)`."""
+    lens = [int(a.shape[0]) for a in arrays]
+    offs, cur = [], 0
+    for n in lens:
+        cur = (cur + align - 1) // align * align
+        offs.append(cur)
+        cur += n
+    tdt = torch.int16 if np.dtype(dtype) == np.int16 else torch.float32
+    stage = torch.empty(max(cur, 1), dtype=tdt, pin_memory=torch.cuda.is_available())
+    view = stage.numpy()
+    prev_end = 0
+    for a, o, n in zip(arrays, offs, lens):
+        view[prev_end:o] = 0
+        view[o:o + n] = a
+        prev_end = o + n
+    return stage, lens, offs

@@ -32,7 +32,7 @@ import numpy as np
 import torch
 
 from .base import FeatureExtractor, register_extractor
-from .engine import OUT_PACKED, OUT_PADDED, Engine, pack_device
+from .engine import OUT_PACKED, OUT_PADDED, Engine, pack_device, stage_host
 from .plan import EPSILON, LOG_EPSILON, FeaturePlan, build_plan
 
 Seconds = float
@@ -315,14 +315,9 @@ class _B200Extractor(FeatureExtractor):
             else:
                 flat = [np.asarray(x).squeeze() for x in items]
                 dt = np.int16 if all(a.dtype == np.int16 for a in flat) else np.float32
-                lens = [int(a.shape[0]) for a in flat]
-                stage = torch.empty(sum(lens), dtype=torch.int16 if dt == np.int16 else torch.float32,
-                                    pin_memory=torch.cuda.is_available())
-                view, o = stage.numpy(), 0
-                for a, n in zip(flat, lens):
-                    view[o:o + n] = a
-                    o += n
-                out, prefix = eng.extract_host(stage, lens)
+                # one pinned staging buffer, every cut on a 4-element boundary (vector-load path of the kernels)
+                stage, lens, offs = stage_host(flat, dtype=dt)
+                out, prefix = eng.extract_host(stage, lens, offsets=offs)
             result = [out[prefix[i]: prefix[i + 1]] for i in range(len(lens))]
         if self._returns_cpu_tensor and input_is_torch:
             result = [r.cpu() for r in result]
@@ -396,6 +391,18 @@ class _B200Extractor(FeatureExtractor):
         out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs, out_mode=OUT_PADDED, pad_value=padding_value)
         feat_lens = torch.from_numpy(np.diff(prefix)).to(torch.int64)
         return out, feat_lens
+
+    def extract_staged_padded(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int,
+                              padding_value: float = LOG_EPSILON):
+        """`extract_batch_padded` for a batch that already sits in ONE (pinned) host buffer — e.g. the int16 PCM ring of
+        `lhotse_b200.pcm_staging`: one H2D copy of the raw bytes, one launch, features stay on the device."""
+        self._check_sr(sampling_rate)
+        eng = self.engine
+        assert staged.dim() == 1 and staged.dtype in (torch.int16, torch.float32)
+        buf = staged.to(eng.device, non_blocking=True)
+        out, prefix = eng.extract_device(self._dithered(buf), list(lens), offsets=list(offsets), out_mode=OUT_PADDED,
+                                         pad_value=padding_value)
+        return out, torch.from_numpy(np.diff(prefix)).to(torch.int64)
 
 
 @register_extractor

@@ -31,6 +31,7 @@ class FusedOnTheFlyFeatures:
         return_audio: bool = False,
         executor_type: Type = ThreadPoolExecutor,
         features_on_device: bool = True,
+        pcm16_fast_path: bool = True,
     ) -> None:
         if not hasattr(extractor, "extract_batch_padded"):
             raise TypeError("FusedOnTheFlyFeatures needs a lhotse_b200 extractor (extract_batch_padded)")
@@ -40,6 +41,12 @@ class FusedOnTheFlyFeatures:
         self.fault_tolerant = fault_tolerant
         self.return_audio = return_audio
         self.features_on_device = features_on_device
+        # §8f-2: when every cut of the batch is a plain slice of a 16-bit PCM WAV file (and nothing has to see the float
+        # waveform: no wave_transforms, no return_audio), the PCM bytes go file -> pinned int16 ring -> GPU, and are
+        # widened inside the kernel (bit-identical to the float route)
+        self.pcm16_fast_path = pcm16_fast_path and hasattr(extractor, "extract_staged_padded")
+        self._ring = None
+        self.last_batch_route = None  # "pcm16" | "float" (introspection for tests / logs)
         self._executor_type = executor_type
         self._executor = None
 
@@ -50,8 +57,40 @@ class FusedOnTheFlyFeatures:
             self._executor = self._executor_type(max_workers=self.num_workers)
         return self._executor
 
+    def _try_pcm16(self, cuts, recording_field):
+        if not self.pcm16_fast_path or self.wave_transforms or self.return_audio or recording_field is not None:
+            return None
+        from .pcm_staging import PcmStagingRing, pcm16_request_for_cut
+
+        reqs = []
+        for c in cuts:
+            r = pcm16_request_for_cut(c)
+            if r is None:
+                return None
+            reqs.append(r)
+        if self._ring is None:
+            self._ring = PcmStagingRing()
+        try:
+            staged, lens, offs, sr = self._ring.stage(reqs, executor=self._get_executor())
+        except (OSError, ValueError):
+            if self.fault_tolerant:
+                return None  # the float route knows how to skip broken cuts
+            raise
+        if sr != cuts[0].sampling_rate:
+            return None
+        return self.extractor.extract_staged_padded(staged, lens, offs, sr, padding_value=LOG_EPSILON)
+
     def __call__(self, cuts, recording_field: Optional[str] = None):
         from lhotse.dataset.collation import collate_vectors, read_audio_from_cuts
+
+        fast = self._try_pcm16(cuts, recording_field)
+        if fast is not None:
+            self.last_batch_route = "pcm16"
+            feats, feat_lens = fast
+            if not self.features_on_device:
+                feats = feats.cpu()
+            return (feats, feat_lens) + ((cuts,) if self.fault_tolerant else ())
+        self.last_batch_route = "float"
 
         audios, cuts = read_audio_from_cuts(
             cuts, executor=self._get_executor(), suppress_errors=self.fault_tolerant, recording_field=recording_field

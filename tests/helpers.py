@@ -96,10 +96,12 @@ class OracleEngine:
         prefix = np.concatenate(([0], np.cumsum([o.shape[0] for o in outs]))).astype(np.int64)
         return outs, prefix
 
-    def extract_host(self, samples, num_samples, out_mode=0, pad_value=0.0, out=None):
+    def extract_host(self, samples, num_samples, out_mode=0, pad_value=0.0, out=None, offsets=None):
         flat = samples.numpy() if isinstance(samples, torch.Tensor) else np.asarray(samples)
         chunks, o = [], 0
-        for n in num_samples:
+        for i, n in enumerate(num_samples):
+            if offsets is not None:
+                o = int(offsets[i])
             chunks.append(flat[o:o + int(n)])
             o += int(n)
         outs, prefix = self._run(chunks)
