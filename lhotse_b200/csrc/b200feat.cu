@@ -446,10 +446,17 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
     if (e != cudaSuccess) return fail(h, B200FEAT_ECUDA, std::string("generic launch: ") + cudaGetErrorString(e));
   }
   if (h->plan.whisper && norm_rows > 0) {  // second launch: clamp to the cut's maximum - 8, (x + 4) / 4, zero rows
-    int64_t blocks = (norm_rows + 7) / 8;
-    const int64_t cap = (int64_t)h->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    b200feat_whisper_normalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h->plan, db, norm_rows);
+    if (h->frames_per_tile > 1) {
+      int64_t blocks = db.num_tiles;
+      const int64_t cap = (int64_t)h->sm_count * 8;
+      if (blocks > cap) blocks = cap;
+      b200feat_whisper_normalize_tiled_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h->plan, db, h->frames_per_tile);
+    } else {
+      int64_t blocks = (norm_rows + 7) / 8;
+      const int64_t cap = (int64_t)h->sm_count * 16;
+      if (blocks > cap) blocks = cap;
+      b200feat_whisper_normalize_kernel<<<(unsigned)blocks, 256, 0, stream>>>(h->plan, db, norm_rows);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, B200FEAT_ECUDA, std::string("whisper normalise launch: ") + cudaGetErrorString(e));
   }

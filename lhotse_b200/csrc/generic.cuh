@@ -253,3 +253,38 @@ __global__ void __launch_bounds__(256) b200feat_whisper_normalize_kernel(const D
     }
   }
 }
+
+
+// The same pass for the tiled kernels (fast400): one CTA per tile of `ft` consecutive rows of one cut, located through the
+// host-built tile -> cut table exactly as the fused kernel does (no per-row search), rows processed as one contiguous run of
+// 128-bit accesses.
+__global__ void __launch_bounds__(256) b200feat_whisper_normalize_tiled_kernel(const DevPlan p, const DevBatch b, int ft) {
+  for (int64_t tg = blockIdx.x; tg < b.num_tiles; tg += gridDim.x) {
+    const int64_t tile = b.tile_base + tg;
+    const int cut = __ldg(b.tile_cut + tile) - b.batch_first;
+    const int64_t t0 = (tile - __ldg(b.tile_off + cut)) * ft;
+    const int64_t T = __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut);
+    const int64_t rows = min((int64_t)ft, T - t0);  // rows past T (padded mode) keep pad_value
+    if (rows <= 0) continue;
+    const int64_t row0 = b.out_mode == B200FEAT_OUT_PADDED ? (int64_t)(b.batch_first + cut) * b.max_frames + t0
+                                                           : __ldg(b.row_off + cut) + t0;
+    const int total = (int)rows * p.F;
+    const int live = (int)max((int64_t)0, min(rows, __ldg(b.nsamp + cut) / p.S - t0)) * p.F;  // floats of stft rows
+    const float thr = b.cut_max[cut] - 8.0f;
+    float *o = b.out + row0 * p.F;
+    if (((row0 * p.F) & 3) == 0 && (p.F & 3) == 0) {
+      float4 *o4 = reinterpret_cast<float4 *>(o);
+      for (int i = threadIdx.x; 4 * i < total; i += blockDim.x) {
+        float4 v = o4[i];
+        const bool on = 4 * i < live;  // F is a multiple of 4: a float4 never straddles the live / zero boundary
+        v.x = on ? (nanmax(v.x, thr) + 4.0f) * 0.25f : 0.f;
+        v.y = on ? (nanmax(v.y, thr) + 4.0f) * 0.25f : 0.f;
+        v.z = on ? (nanmax(v.z, thr) + 4.0f) * 0.25f : 0.f;
+        v.w = on ? (nanmax(v.w, thr) + 4.0f) * 0.25f : 0.f;
+        o4[i] = v;
+      }
+    } else {
+      for (int i = threadIdx.x; i < total; i += blockDim.x) o[i] = i < live ? (nanmax(o[i], thr) + 4.0f) * 0.25f : 0.f;
+    }
+  }
+}

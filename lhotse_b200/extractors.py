@@ -392,6 +392,25 @@ class _B200Extractor(FeatureExtractor):
         feat_lens = torch.from_numpy(np.diff(prefix)).to(torch.int64)
         return out, feat_lens
 
+    def extract_batch_packed(self, samples: Sequence[ArrayLike], sampling_rate: int):
+        """Ragged list -> (packed (sum T_i, F) tensor on the device, int64 row prefix [B + 1]): the kernels' native output
+        layout, for callers that move the whole batch at once (lhotse_b200.storage)."""
+        self._check_sr(sampling_rate)
+        eng = self.engine
+        flat = [(torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x).squeeze() for x in samples]
+        dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
+        buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
+        out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs)
+        return out, np.asarray(prefix, dtype=np.int64)
+
+    def extract_staged_packed(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int):
+        """`extract_batch_packed` for a batch already staged in ONE host buffer (the PCM16 ring)."""
+        self._check_sr(sampling_rate)
+        eng = self.engine
+        buf = staged.to(eng.device, non_blocking=True)
+        out, prefix = eng.extract_device(self._dithered(buf), list(lens), offsets=list(offsets))
+        return out, np.asarray(prefix, dtype=np.int64)
+
     def extract_staged_padded(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int,
                               padding_value: float = LOG_EPSILON):
         """`extract_batch_padded` for a batch that already sits in ONE (pinned) host buffer — e.g. the int16 PCM ring of

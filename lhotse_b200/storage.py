@@ -1,0 +1,230 @@
+"""
+"Next" row §8f-3 of the scope contract: the caller right AFTER the hot path — feature storage fed from the device.
+
+The reference's batch path (`CutSet.compute_and_store_features_batch`, lhotse/cut/set.py:2197-2408) hands the extractor one
+ragged batch and then, per cut: `.cpu().numpy()` (a D2H copy each), `feats_writer.write(cut.id, feat_mat)` (a file or an
+archive entry each), a `Features` manifest, `validate_features`.  With the extraction itself at thousands of hours per
+second that per-cut tail is the whole cost.  Here the batch leaves the GPU as ONE packed `(sum T_i, F)` matrix (the layout
+the kernels write), crosses PCIe once into pinned memory and is appended to ONE archive file with a single `write`;
+the per-cut bookkeeping is reduced to building the manifests.
+
+  * `B200ArchiveWriter` / `B200ArchiveReader` — storage backend "b200_archive": an append-only file of raw little-endian
+    float32 rows; a storage key is "byte offset,rows,cols", so a reader slices frames without any index.  They implement
+    lhotse's `FeaturesWriter` / `FeaturesReader` interfaces (features/io.py:26-176) and register in its backend registries
+    (io.py:283-313) when lhotse is importable: `Features.load`, `cut.load_features()`, partial reads all work unchanged.
+  * `compute_and_store_features_fused(cuts, extractor, storage_path, ...)` — the counterpart of
+    `compute_and_store_features_batch` (same arguments where they apply, same resumable manifest writer, same `Features`
+    fields, PaddingCut / MixedCut handling as set.py:2306-2362) on top of `extract_batch_packed`, the PCM16 ring of
+    `pcm_staging` when the cuts allow it, and `write_batch`.
+Not built: a lilcom-compatible quantiser (`LilcomChunkyWriter`, io.py:982): lilcom is an un-vendored optional dependency that
+cannot be installed here, so its bit format could not be pinned; the archive is lossless float32 instead.
+"""
+from __future__ import annotations
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+try:  # pragma: no cover - depends on the environment
+    from lhotse.features.io import FeaturesReader, FeaturesWriter, register_reader, register_writer
+
+    HAVE_LHOTSE_IO = True
+except Exception:
+    HAVE_LHOTSE_IO = False
+    FeaturesReader = FeaturesWriter = object
+
+    def register_reader(cls):
+        return cls
+
+    def register_writer(cls):
+        return cls
+
+
+ARCHIVE_SUFFIX = ".b200feat"
+
+
+def _archive_path(storage_path) -> str:
+    p = str(storage_path)
+    return p if p.endswith(ARCHIVE_SUFFIX) else p + ARCHIVE_SUFFIX
+
+
+@register_writer
+class B200ArchiveWriter(FeaturesWriter):
+    """Append-only archive of float32 feature matrices.  `mode="w"` truncates, `"a"` appends (keys stay valid: they are
+    absolute byte offsets).  One `write_batch` = one `write` system call for the whole batch."""
+
+    name = "b200_archive"
+
+    def __init__(self, storage_path, mode: str = "w", *args, **kwargs):
+        assert mode in ("w", "a"), mode
+        self._path = _archive_path(storage_path)
+        Path(self._path).parent.mkdir(parents=True, exist_ok=True)
+        self._f = open(self._path, "wb" if mode == "w" else "ab")
+        self._pos = self._f.seek(0, os.SEEK_END)
+
+    @property
+    def storage_path(self) -> str:
+        return self._path
+
+    def write(self, key: str, value: np.ndarray) -> str:
+        value = np.ascontiguousarray(value, dtype="<f4")
+        if value.ndim != 2:
+            raise ValueError(f"b200_archive stores (frames, features) matrices, got shape {value.shape}")
+        off = self._pos
+        self._f.write(memoryview(value).cast("B"))
+        self._pos += value.nbytes
+        return f"{off},{value.shape[0]},{value.shape[1]}"
+
+    def write_batch(self, keys: Sequence[str], packed: np.ndarray, row_prefix: Sequence[int]) -> List[str]:
+        """`packed`: (sum T_i, F) float32 with cut i in rows row_prefix[i]:row_prefix[i+1] (what `extract_batch_packed`
+        returns after ONE device-to-host copy).  Appends it with a single write and returns the per-cut storage keys."""
+        packed = np.ascontiguousarray(packed, dtype="<f4")
+        assert packed.ndim == 2 and len(row_prefix) == len(keys) + 1 and int(row_prefix[-1]) == packed.shape[0]
+        base, F = self._pos, packed.shape[1]
+        self._f.write(memoryview(packed).cast("B"))
+        self._pos += packed.nbytes
+        return [f"{base + int(row_prefix[i]) * F * 4},{int(row_prefix[i + 1]) - int(row_prefix[i])},{F}" for i in range(len(keys))]
+
+    def flush(self):
+        self._f.flush()
+
+    def close(self):
+        if not self._f.closed:
+            self._f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *args, **kwargs):
+        self.close()
+
+
+@register_reader
+class B200ArchiveReader(FeaturesReader):
+    name = "b200_archive"
+
+    def __init__(self, storage_path, *args, **kwargs):
+        self._path = _archive_path(storage_path)
+        self._fd = None
+
+    def _file(self):
+        if self._fd is None:
+            self._fd = os.open(self._path, os.O_RDONLY)
+        return self._fd
+
+    def read(self, key: str, left_offset_frames: int = 0, right_offset_frames: Optional[int] = None) -> np.ndarray:
+        off, rows, cols = (int(v) for v in key.split(","))
+        hi = rows if right_offset_frames is None else min(rows, right_offset_frames)
+        lo = max(0, left_offset_frames)
+        n = max(0, hi - lo)
+        out = np.empty((n, cols), dtype=np.float32)
+        if n:
+            view, got, pos = memoryview(out).cast("B"), 0, off + lo * cols * 4
+            while got < len(view):
+                k = os.preadv(self._file(), [view[got:]], pos + got)
+                if k <= 0:
+                    raise IOError(f"{self._path}: short read at {pos + got}")
+                got += k
+        return out
+
+    def __del__(self):
+        try:
+            if self._fd is not None:
+                os.close(self._fd)
+        except Exception:
+            pass
+
+
+def compute_and_store_features_fused(
+    cuts,
+    extractor,
+    storage_path,
+    manifest_path=None,
+    batch_duration: float = 600.0,
+    num_workers: int = 4,
+    overwrite: bool = False,
+    pcm16_fast_path: bool = True,
+):
+    """`CutSet.compute_and_store_features_batch(extractor, storage_path, manifest_path, batch_duration, num_workers,
+    overwrite=...)` (lhotse/cut/set.py:2197-2408) with the batch kept whole from the GPU to the disk: one packed
+    extraction, one D2H copy, one archive append per batch.  Returns the CutSet with `Features` attached (lazy when
+    `manifest_path` is given, resumable exactly like the reference: cut ids already in the manifest are skipped)."""
+    from lhotse import CutSet
+    from lhotse.cut import MixedCut, MonoCut, PaddingCut
+    from lhotse.cut.data import DataCut
+    from lhotse.dataset.collation import read_audio_from_cuts
+    from lhotse.dataset.sampling import SimpleCutSampler
+    from lhotse.features.base import Features
+    from lhotse.qa import validate_features
+    from lhotse.utils import fastcopy
+
+    from .pcm_staging import PcmStagingRing, pcm16_request_for_cut
+
+    frame_shift = extractor.frame_shift
+    cuts_writer = CutSet.open_writer(manifest_path, overwrite=overwrite)
+    sampler = SimpleCutSampler(cuts, max_duration=batch_duration)
+    sampler.filter(lambda cut: cut.id not in cuts_writer.ignore_ids)
+    ring = PcmStagingRing() if pcm16_fast_path and hasattr(extractor, "extract_staged_packed") else None
+    pool = ThreadPoolExecutor(max_workers=num_workers) if num_workers > 0 else None
+
+    def _save(batch_cuts, feats: np.ndarray, prefix, keys):
+        for i, cut in enumerate(batch_cuts):
+            rows = int(prefix[i + 1] - prefix[i])
+            if isinstance(cut, PaddingCut):  # set.py:2307-2318: manifest fields only
+                cuts_writer.write(fastcopy(cut, num_frames=rows, num_features=feats.shape[1], frame_shift=frame_shift))
+                continue
+            fm = Features(
+                start=cut.start, duration=cut.duration, type=extractor.name, num_frames=rows, num_features=feats.shape[1],
+                frame_shift=frame_shift, sampling_rate=cut.sampling_rate, channels=cut.channel,
+                storage_type=writer.name, storage_path=str(writer.storage_path), storage_key=keys[i],
+            )
+            validate_features(fm, feats_data=feats[prefix[i]: prefix[i + 1]])
+            if isinstance(cut, DataCut):
+                fm.recording_id = cut.recording_id
+                cut = fastcopy(cut, features=fm)
+            if isinstance(cut, MixedCut):  # set.py:2344-2361
+                fm.recording_id = cut.id
+                cut = MonoCut(id=cut.id, start=0, duration=cut.duration, channel=0,
+                              supervisions=[fastcopy(s, recording_id=cut.id, channel=0) for s in cut.supervisions],
+                              features=fm, recording=None)
+            cuts_writer.write(cut, flush=True)
+
+    with cuts_writer, B200ArchiveWriter(storage_path, mode="w" if overwrite else "a") as writer, \
+            ThreadPoolExecutor(max_workers=1) as saver:  # one background saver: deterministic manifest order
+        futures = []
+        for batch in sampler:
+            batch_cuts = list(batch)
+            if not batch_cuts:
+                continue
+            sr = batch_cuts[0].sampling_rate
+            assert all(c.sampling_rate == sr for c in batch_cuts)
+            packed = prefix = None
+            if ring is not None:
+                reqs = [pcm16_request_for_cut(c) for c in batch_cuts]
+                if all(r is not None for r in reqs):
+                    staged, lens, offs, fsr = ring.stage(reqs, executor=pool)
+                    if fsr == sr:
+                        packed, prefix = extractor.extract_staged_packed(staged, lens, offs, sr)
+            if packed is None:
+                audios, batch_cuts = read_audio_from_cuts(batch_cuts, executor=pool)
+                if not batch_cuts:
+                    continue
+                packed, prefix = extractor.extract_batch_packed(audios, sr)
+            # ONE device-to-host copy of the batch, into pinned memory when there is a GPU
+            if isinstance(packed, torch.Tensor):
+                if packed.is_cuda:
+                    host = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+                    host.copy_(packed, non_blocking=False)
+                    packed = host
+                packed = packed.numpy()
+            keys = writer.write_batch([c.id for c in batch_cuts], packed, prefix)
+            futures.append(saver.submit(_save, batch_cuts, packed, prefix, keys))
+        for f in futures:
+            f.result()
+    if pool is not None:
+        pool.shutdown()
+    return cuts_writer.open_manifest()

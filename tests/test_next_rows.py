@@ -105,3 +105,55 @@ def test_rank_sharded_extraction_roundtrip(env):
         assert c.has_features and c.features.type == "b200-fbank"
         f = c.load_features()
         assert f.shape == (c.num_frames, 80)
+
+
+def test_archive_backend_and_fused_store(env, tmp_path):
+    """§8f-3: the b200_archive backend behind lhotse's reader/writer registries, and compute_and_store_features_fused
+    against the reference's own compute_and_store_features_batch on the same cuts."""
+    from helpers import attach_oracle_engine
+    from lhotse import CutSet
+    from lhotse.features.io import NumpyFilesWriter, get_reader, get_writer
+
+    from lhotse_b200.storage import B200ArchiveReader, B200ArchiveWriter, compute_and_store_features_fused
+
+    assert get_writer("b200_archive") is B200ArchiveWriter and get_reader("b200_archive") is B200ArchiveReader
+    # backend contract: write / write_batch / partial reads / append
+    rs = np.random.RandomState(0)
+    a, b, c = (rs.randn(t, 80).astype(np.float32) for t in (100, 37, 250))
+    with B200ArchiveWriter(tmp_path / "arch") as w:
+        ka = w.write("a", a)
+        kb, kc = w.write_batch(["b", "c"], np.concatenate([b, c]), [0, 37, 287])
+        assert w.storage_path.endswith(".b200feat")
+    r = B200ArchiveReader(tmp_path / "arch")
+    assert np.array_equal(r.read(ka), a) and np.array_equal(r.read(kb), b) and np.array_equal(r.read(kc), c)
+    assert np.array_equal(r.read(kc, left_offset_frames=10, right_offset_frames=60), c[10:60])
+    assert r.read(kc, left_offset_frames=250).shape == (0, 80)
+    with B200ArchiveWriter(tmp_path / "arch", mode="a") as w:
+        kd = w.write("d", a[:5])
+    r2 = B200ArchiveReader(tmp_path / "arch")
+    assert np.array_equal(r2.read(kd), a[:5]) and np.array_equal(r2.read(ka), a)  # old keys survive an append
+    ta = w.__class__(tmp_path / "arr").store_array("k", b, frame_shift=0.01, temporal_dim=0)  # lhotse's Array manifests
+    assert np.array_equal(ta.load(), b)
+
+    cuts, lb_ex, root = env
+    ext = attach_oracle_engine(lb_ex.B200Fbank())
+    want = cuts.compute_and_store_features_batch(ext, root / "ref_store", num_workers=0, batch_duration=4.0,
+                                                 storage_type=NumpyFilesWriter, overwrite=True)
+    for route in (True, False):
+        got = compute_and_store_features_fused(cuts, ext, root / f"fused_{route}", manifest_path=root / f"fused_{route}.jsonl.gz",
+                                               batch_duration=4.0, num_workers=2, overwrite=True, pcm16_fast_path=route)
+        got = CutSet.from_cuts(list(got))
+        assert [c_.id for c_ in got] == [c_.id for c_ in want]
+        for g, w_ in zip(got, want):
+            assert g.has_features and g.features.storage_type == "b200_archive" and g.features.type == "b200-fbank"
+            assert (g.num_frames, g.num_features, g.features.recording_id) == (w_.num_frames, w_.num_features, w_.features.recording_id)
+            assert np.array_equal(g.load_features(), w_.load_features())
+            part = g.features.load(start=g.start + 0.2, duration=0.3)
+            assert np.array_equal(part, w_.features.load(start=w_.start + 0.2, duration=0.3))
+    # resumable like the reference: a second call with the same manifest does not recompute anything
+    calls = []
+    orig = ext.extract_batch_packed
+    ext.extract_batch_packed = lambda *a_, **k_: calls.append(1) or orig(*a_, **k_)
+    again = compute_and_store_features_fused(cuts, ext, root / "fused_False", manifest_path=root / "fused_False.jsonl.gz",
+                                             batch_duration=4.0, num_workers=0, pcm16_fast_path=False)
+    assert len(list(again)) == len(cuts) and not calls

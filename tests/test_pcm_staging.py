@@ -207,3 +207,32 @@ def test_gpu_staged_pcm16_equals_float_and_aligned_host_staging(tmp_path):
     assert np.array_equal(a, b)
     with pytest.raises(lb.B200FeatError):
         eng.extract_host(buf, blens, offsets=[0, 10, 20, 30, 40, 50])  # overlapping
+
+
+@pytest.mark.gpu
+def test_gpu_packed_batch_to_archive_roundtrip(tmp_path):
+    """§8f-3 on the device: one packed extraction, ONE device-to-host copy, ONE archive append; every cut reads back equal
+    to its own `extract` (the archive backend itself needs no lhotse)."""
+    import lhotse_b200 as lb
+    from lhotse_b200.storage import B200ArchiveReader, B200ArchiveWriter
+
+    rs = np.random.RandomState(12)
+    xs = [(0.1 * rs.randn(n)).astype(np.float32) for n in (16000, 4001, 23457, 801, 48000)]
+    for ext in (lb.B200Fbank(), lb.B200Mfcc(), lb.B200WhisperFbank()):
+        packed, prefix = ext.extract_batch_packed(xs, 16000)
+        assert packed.is_cuda and packed.shape == (int(prefix[-1]), ext.feature_dim(16000)) and prefix[0] == 0
+        host = torch.empty(packed.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(packed)
+        with B200ArchiveWriter(tmp_path / ext.name) as w:
+            keys = w.write_batch([f"c{i}" for i in range(len(xs))], host.numpy(), prefix)
+        r = B200ArchiveReader(tmp_path / ext.name)
+        for x, k in zip(xs, keys):
+            want = ext.extract(x, 16000)
+            assert np.array_equal(r.read(k), want)
+            assert np.array_equal(r.read(k, 3, 9), want[3:9])
+    pcm = [np.clip(x * 32768, -32768, 32767).astype(np.int16) for x in xs]
+    buf, lens, offs = stage_host(pcm, dtype=np.int16)
+    ext = lb.B200Fbank()
+    a, pa = ext.extract_staged_packed(buf, lens, offs, 16000)
+    b, pb = ext.extract_batch_packed([p.astype(np.float32) / 32768.0 for p in pcm], 16000)
+    assert np.array_equal(pa, pb) and torch.equal(a, b)
