@@ -102,7 +102,8 @@ typedef struct b200feat_plan_desc {
   float preemph_coeff;  /* 0 disables, layers.py:165 */
   float energy_floor;   /* linear-domain floor (EPSILON = 1e-10 by default) */
   float mel_floor;      /* clamp before log for fbank/mfcc: finfo(float32).eps, layers.py:572 */
-  float log_spec_eps;   /* additive eps of the log-spectrogram: 1e-15, layers.py:467 */
+  float log_spec_eps;   /* log-spectrogram: eps >= 0 -> log(P + eps) (1e-15, layers.py:467); a negative value -f selects the
+                           Kaldi / torchaudio form log(max(P, f)) (torchaudio/compliance/kaldi.py spectrogram, f = eps32) */
 } b200feat_plan_desc;
 
 typedef struct b200feat_handle b200feat_handle; /* opaque */

@@ -26,6 +26,8 @@ from .families import (  # noqa: F401
     B200TorchaudioFbankConfig,
     B200TorchaudioMfcc,
     B200TorchaudioMfccConfig,
+    B200TorchaudioSpectrogram,
+    B200TorchaudioSpectrogramConfig,
 )
 from .engine import Engine, B200FeatError, load_library  # noqa: F401
 

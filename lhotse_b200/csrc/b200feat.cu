@@ -179,7 +179,9 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
                                                                       : desc->energy_floor > 0.f;
   p.has_energy_floor = has_floor ? 1.f : 0.f;
   p.energy_floor_log = has_floor ? (float)log((double)desc->energy_floor) : 0.f;
-  p.mel_floor = desc->mel_floor; p.log_spec_eps = desc->log_spec_eps;
+  p.mel_floor = desc->mel_floor;
+  p.log_spec_eps = desc->log_spec_eps < 0.f ? 0.f : desc->log_spec_eps;
+  p.log_spec_floor = desc->log_spec_eps < 0.f ? -desc->log_spec_eps : 0.f;
   switch (desc->feature) {
     case B200FEAT_FBANK: p.F = p.M + (desc->use_energy ? 1 : 0); break;
     case B200FEAT_WHISPER_FBANK: p.F = p.M; break;

@@ -22,6 +22,7 @@ struct DevPlan {
   int nstages;
   int radix[B200_MAX_STAGES];
   float preemph, energy_floor_log, has_energy_floor, mel_floor, log_spec_eps;
+  float log_spec_floor;             // > 0: log-spectrogram as log(max(P, floor)) (torchaudio kaldi.py spectrogram) instead of log(P + eps)
   const float *window;   // [L]
   const float2 *tw;      // [Nc]   exp(-2 pi i k / Nc)
   const float2 *tws;     // [N/2+1] exp(-2 pi i k / N) (packed split), even N only
@@ -109,6 +110,11 @@ __device__ __forceinline__ float fast_lg2_normal(float x) {
   return r;
 }
 __device__ __forceinline__ float fast_log_normal(float x) { return fast_lg2_normal(x) * 0.69314718055994530942f; }
+
+// one bin of the log-spectrogram: lhotse log(P + 1e-15) (layers.py:467) or Kaldi/torchaudio log(max(P, eps32))
+__device__ __forceinline__ float log_spec_value(const DevPlan &p, float x) {
+  return p.log_spec_floor > 0.f ? logf(nanmax(x, p.log_spec_floor)) : logf(x + p.log_spec_eps);
+}
 
 __device__ __forceinline__ float log_energy_value(const DevPlan &p, float e) {
   float le;

@@ -272,7 +272,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         if (f >= nvalid) { for (int k = lane; k < p.F; k += 32) o[k] = b.pad_value; continue; }
         for (int k = lane; k < p.K; k += 32) {
           float x = P[f * F1K_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
-          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
+          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
           if (k == 0 && p.use_energy) {
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) x = (f == g) ? le[g] : x;

@@ -289,7 +289,7 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
         if (f >= nvalid) { for (int k = l; k < p.F; k += 8) o[k] = b.pad_value; continue; }
         for (int k = l; k < p.K; k += 8) {
           float x = P[f * F256_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
-          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
+          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
           if (k == 0 && p.use_energy) {
 #pragma unroll
             for (int q = 0; q < F256_SLOTS; ++q) x = (f == q) ? le[q] : x;

@@ -284,7 +284,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
         if (f >= nvalid) { for (int k = l; k < p.F; k += 8) o[k] = b.pad_value; continue; }
         for (int k = l; k < p.K; k += 8) {
           float x = P[f * F400_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
-          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
+          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
           if (k == 0 && p.use_energy) {
 #pragma unroll
             for (int g = 0; g < F400_SLOTS; ++g) x = (f == g) ? le[g] : x;

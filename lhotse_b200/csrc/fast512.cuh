@@ -439,7 +439,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         if (f >= nvalid) { for (int k = l; k < p.F; k += 16) o[k] = b.pad_value; continue; }
         for (int k = l; k < p.K; k += 16) {
           float x = P[f * PBINS + k] * (p.use_mag ? 0.5f : 0.25f);  // P holds |2X|^2 (or |2X|)
-          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = logf(x + p.log_spec_eps);
+          if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
           if (k == 0 && p.use_energy) {
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) x = (f == g) ? le[g] : x;

@@ -344,7 +344,7 @@ b200feat_fast512x2_kernel(const DevPlan p, const FastX2Tables ft, const DevBatch
         for (int k = l; k < p.K; k += 16) {
           const float2 pw = P[k];
           float xa = pw.x * sc, xb = pw.y * sc;
-          if (p.feature == B200FEAT_LOG_SPECTROGRAM) { xa = logf(xa + p.log_spec_eps); xb = logf(xb + p.log_spec_eps); }
+          if (p.feature == B200FEAT_LOG_SPECTROGRAM) { xa = log_spec_value(p, xa); xb = log_spec_value(p, xb); }
           if (k == 0 && p.use_energy) { xa = le2.x; xb = le2.y; }
           if (vA) outA[k] = xa; else if (rA) outA[k] = b.pad_value;
           if (vB) outB[k] = xb; else if (rB) outB[k] = b.pad_value;

@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
       for (int k = lane; k < p.K; k += 32) out[k] = (k == 0 && p.use_energy) ? le : raw[k];
     } else if (p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int k = lane; k < p.K; k += 32)
-        out[k] = (k == 0 && p.use_energy) ? le : logf(raw[k] + p.log_spec_eps);
+        out[k] = (k == 0 && p.use_energy) ? le : log_spec_value(p, raw[k]);
     } else {
       float *mlog = reinterpret_cast<float *>(dst);  // scratch (FFT buffer not holding the result)
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;

@@ -138,6 +138,7 @@ class B200SpectrogramConfig(_ConfigMixin):
     use_fft_mag: bool = False
     device: str = "cuda"
     kernel: str = "auto"
+    compat: str = "lhotse"  # "torchaudio" (log-spectrogram only): log(max(P, eps32)), Kaldi log-energy in bin 0 (TorchaudioSpectrogram)
 
 
 @dataclass

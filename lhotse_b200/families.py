@@ -5,6 +5,9 @@ Registry-level drop-ins for the two other config families of the same Kaldi arit
     ------------------------------------------------------------------------------------------------
     TorchaudioFbank   lhotse/features/fbank.py:42      "fbank"             B200TorchaudioFbank   "b200-torchaudio-fbank"
     TorchaudioMfcc    lhotse/features/mfcc.py:42       "mfcc"              B200TorchaudioMfcc    "b200-torchaudio-mfcc"
+    TorchaudioSpectrogram lhotse/features/spectrogram.py:35 "spectrogram"  B200TorchaudioSpectrogram "b200-torchaudio-spectrogram"
+      (torchaudio's "spectrogram" is a LOG-power spectrum log(max(|X|^2, eps32)) whose bin 0 always carries the Kaldi
+       log-energy: the log-spectrogram kernels with `log_spec_eps = -eps32` and `use_energy`)
     KaldifeatFbank    lhotse/features/kaldifeat.py:178 "kaldifeat-fbank"   B200KaldifeatFbank    "b200-kaldifeat-fbank"
     KaldifeatMfcc     lhotse/features/kaldifeat.py:249 "kaldifeat-mfcc"    B200KaldifeatMfcc     "b200-kaldifeat-mfcc"
 
@@ -20,8 +23,7 @@ Family-specific behaviour kept from the reference:
   * kaldifeat's `extract` takes a single waveform OR a list / 2-D batch of waveforms and `extract_batch(..., lengths)`
     trims and forwards to it (kaldifeat.py:78-141); numpy in -> numpy out, tensors in -> tensors on the device.
 Not supported (raise ValueError at construction / first use): `vtln_warp != 1`, `min_duration != 0`, `htk_compat=True`,
-`use_log_fbank=False`, `htk_mode=True`.  `TorchaudioSpectrogram` (a log-power spectrogram with a max() floor instead of the
-additive epsilon of `LogSpectrogram`) has no adapter yet.
+`use_log_fbank=False`, `htk_mode=True`.
 kaldifeat itself is an un-vendored, unpinned optional dependency (setup.py:188) that cannot be installed here: its parity
 is anchored, as in the reference's own test (test/features/test_kaldifeat_features.py:103-116), on agreement with `Fbank` /
 `Mfcc`; the torchaudio family is pinned by tests/golden/golden_torchaudio_v1.npz.
@@ -36,7 +38,7 @@ import numpy as np
 import torch
 
 from .base import FeatureExtractor, register_extractor
-from .extractors import B200Fbank, from_reference_config
+from .extractors import B200Fbank, B200LogSpectrogram, B200LogSpectrogramConfig, from_reference_config
 from .plan import EPSILON
 
 Seconds = float
@@ -83,6 +85,31 @@ class B200TorchaudioMfccConfig(B200TorchaudioFbankConfig):
     num_mel_bins: int = 23
     cepstral_lifter: float = 22.0
     num_ceps: int = 13
+
+
+@dataclass
+class B200TorchaudioSpectrogramConfig:
+    """Field-for-field TorchaudioSpectrogramConfig (spectrogram.py:11-31) + device / kernel."""
+
+    dither: float = 0.0
+    window_type: str = "povey"
+    frame_length: Seconds = 0.025
+    frame_shift: Seconds = 0.01
+    remove_dc_offset: bool = True
+    round_to_power_of_two: bool = True
+    energy_floor: float = EPSILON
+    min_duration: float = 0.0
+    preemphasis_coefficient: float = 0.97
+    raw_energy: bool = True
+    device: str = "cuda"
+    kernel: str = "auto"
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any]):
+        return cls(**data)
 
 
 @dataclass
@@ -276,6 +303,35 @@ class B200TorchaudioMfcc(_TorchaudioFamily):
     scale = staticmethod(FeatureExtractor.scale)
 
 
+@register_extractor
+class B200TorchaudioSpectrogram(_TorchaudioFamily):
+    name = "b200-torchaudio-spectrogram"
+    config_type = B200TorchaudioSpectrogramConfig
+
+    def _inner(self, sampling_rate: int):
+        sr = int(sampling_rate)
+        inner = self._inner_by_sr.get(sr)
+        if inner is None:
+            c = self.config
+            inner = B200LogSpectrogram(B200LogSpectrogramConfig(
+                sampling_rate=sr, frame_length=c.frame_length, frame_shift=c.frame_shift,
+                round_to_power_of_two=c.round_to_power_of_two, remove_dc_offset=c.remove_dc_offset,
+                preemph_coeff=c.preemphasis_coefficient, window_type=c.window_type, dither=c.dither,
+                energy_floor=c.energy_floor, raw_energy=c.raw_energy, use_energy=True,  # kaldi.py: bin 0 <- log-energy, always
+                device=str(c.device), kernel=c.kernel, compat="torchaudio"))
+            self._inner_by_sr[sr] = inner
+        return inner
+
+    def extract(self, samples: ArrayLike, sampling_rate: int) -> np.ndarray:
+        feats = self._inner(sampling_rate).extract(samples, sampling_rate)
+        return feats.cpu().numpy() if isinstance(feats, torch.Tensor) else feats
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self._inner(sampling_rate).plan.K  # (the reference's non-power-of-two branch, spectrogram.py:52-57, returns L)
+
+    # log-power spectra: logsumexp mixing, spectrogram.py:60-78 — the same formulas as the log-mel statics above
+
+
 class _KaldifeatFamily(_FamilyExtractor):
     def _validate(self):
         if getattr(self.config.mel_opts, "htk_mode", False):
@@ -327,6 +383,6 @@ class B200KaldifeatMfcc(_KaldifeatFamily):
 
 
 FAMILY_ALIASES = {
-    "fbank": B200TorchaudioFbank, "mfcc": B200TorchaudioMfcc,
+    "fbank": B200TorchaudioFbank, "mfcc": B200TorchaudioMfcc, "spectrogram": B200TorchaudioSpectrogram,
     "kaldifeat-fbank": B200KaldifeatFbank, "kaldifeat-mfcc": B200KaldifeatMfcc,
 }

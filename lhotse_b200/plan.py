@@ -300,6 +300,9 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
         energy_floor=float(_get(cfg, "energy_floor", default=EPSILON)),
         dither=dither,
     )
+    if feature == "log-spectrogram" and is_torchaudio:
+        # torchaudio.compliance.kaldi.spectrogram: log(max(|X|^2, eps32)) — a negative log_spec_eps selects the floor form
+        plan.log_spec_eps = -float(torch.finfo(torch.float).eps)
     plan.window = make_window(
         L, window_type, blackman_coeff=float(_get(frame, "blackman_coeff", default=0.42)),
         torchaudio_blackman=is_torchaudio or is_kaldifeat,

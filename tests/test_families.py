@@ -35,6 +35,15 @@ def _ta_golden():
 TA_GOLD = _ta_golden()
 
 
+def _ta_spec_golden():
+    g = np.load(os.path.join(HERE, "golden", "golden_torchaudio_spec_v1.npz"))
+    man = json.loads(bytes(g["manifest"]).decode())
+    return [(i, c, g[f"x{i}"], g[f"y{i}"]) for i, c in enumerate(man)]
+
+
+TA_SPEC_GOLD = _ta_spec_golden()
+
+
 # ------------------------------------------------------------------------------------------------ CPU tier
 @pytest.mark.reference
 @pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")
@@ -44,9 +53,11 @@ def test_config_surfaces_match_the_reference_field_for_field():
     from lhotse.features.kaldifeat import (KaldifeatFbankConfig, KaldifeatFrameOptions, KaldifeatMelOptions,
                                            KaldifeatMfccConfig)
     from lhotse.features.mfcc import TorchaudioMfccConfig
+    from lhotse.features.spectrogram import TorchaudioSpectrogramConfig
 
     _, fam = _lb()
     pairs = [(TorchaudioFbankConfig, fam.B200TorchaudioFbankConfig), (TorchaudioMfccConfig, fam.B200TorchaudioMfccConfig),
+             (TorchaudioSpectrogramConfig, fam.B200TorchaudioSpectrogramConfig),
              (KaldifeatFrameOptions, fam.B200KaldifeatFrameOptions), (KaldifeatMelOptions, fam.B200KaldifeatMelOptions),
              (KaldifeatFbankConfig, fam.B200KaldifeatFbankConfig), (KaldifeatMfccConfig, fam.B200KaldifeatMfccConfig)]
     for ref_cls, our_cls in pairs:
@@ -74,7 +85,7 @@ def test_family_registry_names_and_round_trips(tmp_path):
     saved = dict(_REGISTRY)
     try:
         lhotse_b200.install_as_default()
-        for name, cls in (("fbank", "B200TorchaudioFbank"), ("mfcc", "B200TorchaudioMfcc"),
+        for name, cls in (("fbank", "B200TorchaudioFbank"), ("mfcc", "B200TorchaudioMfcc"), ("spectrogram", "B200TorchaudioSpectrogram"),
                           ("kaldifeat-fbank", "B200KaldifeatFbank"), ("kaldifeat-mfcc", "B200KaldifeatMfcc")):
             assert get_extractor_type(name).__name__ == cls
         # a manifest / YAML produced by the reference ("feature_type: kaldifeat-fbank", device: cpu, ms spellings)
@@ -88,7 +99,11 @@ def test_family_registry_names_and_round_trips(tmp_path):
     finally:
         _REGISTRY.clear()
         _REGISTRY.update(saved)
-    for cls in (fam.B200TorchaudioFbank, fam.B200TorchaudioMfcc, fam.B200KaldifeatFbank, fam.B200KaldifeatMfcc):
+    sp = fam.B200TorchaudioSpectrogram()
+    plan = sp._inner(16000).plan  # kaldi.py spectrogram: log(max(P, eps32)), bin 0 <- Kaldi log-energy
+    assert (plan.feature, plan.use_energy, plan.energy_style, sp.feature_dim(16000), sp.feature_dim(8000)) == ("log-spectrogram", True, 1, 257, 129)
+    assert plan.log_spec_eps == -float(np.finfo(np.float32).eps)
+    for cls in (fam.B200TorchaudioFbank, fam.B200TorchaudioMfcc, fam.B200TorchaudioSpectrogram, fam.B200KaldifeatFbank, fam.B200KaldifeatMfcc):
         ext = cls()
         path = tmp_path / f"{cls.name}.yml"
         ext.to_yaml(path)
@@ -176,3 +191,25 @@ def test_gpu_kaldifeat_adapters_agree_with_fbank_and_mfcc():
     k8 = fam.B200KaldifeatFbank.config_type.from_dict({"frame_opts": {"samp_freq": 8000.0}, "mel_opts": {"num_bins": 40}})
     y8 = fam.B200KaldifeatFbank(k8).extract(xs[0][:8000], 8000)
     assert y8.shape == (100, 40) and np.isfinite(y8).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i,c,x,y", TA_SPEC_GOLD, ids=[f"{i}-sr{c['sampling_rate']}" for i, c, _, _ in TA_SPEC_GOLD])
+@pytest.mark.parametrize("kernel", ["auto", "generic"])
+def test_gpu_torchaudio_spectrogram_adapter_golden(kernel, i, c, x, y):
+    """`torchaudio.compliance.kaldi.spectrogram` (tests/golden/make_golden_torchaudio_spectrogram.py) through
+    B200TorchaudioSpectrogram.  Bin 0 is a Kaldi log-energy (compared directly); the other bins are log(max(P, eps32)):
+    compared as amplitudes, because an fp32 FFT carries an error ~1e-6 of the frame's largest line whatever the bin's own
+    size (the rule of helpers.gate), and checked to sit on the same floor where the reference does."""
+    _, fam = _lb()
+    ext = fam.B200TorchaudioSpectrogram(fam.B200TorchaudioSpectrogramConfig.from_dict(dict(c["cfg"], kernel=kernel)))
+    got = ext.extract(x, c["sampling_rate"])
+    assert isinstance(got, np.ndarray) and got.shape == y.shape and np.isfinite(got).all()
+    np.testing.assert_allclose(got[:, 0], y[:, 0], rtol=1e-4, atol=2e-4)
+    floor = np.log(np.float32(np.finfo(np.float32).eps))
+    assert got[:, 1:].min() >= floor - 1e-6
+    silent = (y[:, 1:] <= floor + 1e-6).all(axis=1)   # frames of exact silence: every bin on the floor, in both
+    np.testing.assert_allclose(got[silent, 1:], y[silent, 1:], rtol=0, atol=4e-6)  # logf(eps32): device vs host libm
+    a_got, a_ref = np.exp(0.5 * got[:, 1:].astype(np.float64)), np.exp(0.5 * y[:, 1:].astype(np.float64))
+    tol = 1e-4 * a_ref + 4e-6 * a_ref.max(axis=1, keepdims=True) + 1e-9
+    assert (np.abs(a_got - a_ref) <= tol).all(), float((np.abs(a_got - a_ref) / tol).max())
