@@ -30,9 +30,9 @@ __device__ __forceinline__ void dft8(float2 &x0, float2 &x1, float2 &x2, float2 
   float2 e0 = x0, e1 = x2, e2 = x4, e3 = x6, o0 = x1, o1 = x3, o2 = x5, o3 = x7;
   dft4(e0, e1, e2, e3);
   dft4(o0, o1, o2, o3);
-  o1 = f2mul(o1, make_float2(F512_R2, -F512_R2));   // W8^1
+  o1 = f2mul_w8_1(o1);                              // W8^1
   o2 = f2mi(o2);                                    // W8^2 = -i
-  o3 = f2mul(o3, make_float2(-F512_R2, -F512_R2));  // W8^3
+  o3 = f2mul_w8_3(o3);                              // W8^3
   x0 = f2add(e0, o0); x4 = f2sub(e0, o0);
   x1 = f2add(e1, o1); x5 = f2sub(e1, o1);
   x2 = f2add(e2, o2); x6 = f2sub(e2, o2);

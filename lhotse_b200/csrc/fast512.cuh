@@ -105,19 +105,40 @@ __device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 
 #define F512_S1 0.38268343236508977f  // sin(pi/8)
 #define F512_R2 0.70710678118654752f  // sqrt(1/2)
 
+// Multiplications by the eighth roots of unity W8^1 = (1 - i)/sqrt2 and W8^3 = -(1 + i)/sqrt2: a*(1 -+ i) is ONE packed add
+// with a rotated operand (a + (-i)a resp. a + (+i)a, the rotation rides on the FADD2 operand modifiers) and the scale is
+// ONE packed multiply: 2 issue slots instead of the 4 (2 FMUL + 2 FFMA) of a general complex product.
+#ifndef F512_R2TRICK
+#define F512_R2TRICK 1
+#endif
+__device__ __forceinline__ float2 f2mul_w8_1(float2 a) {
+#if F512_R2TRICK && F512_PACKED
+  return __fmul2_rn(f2add(a, f2mi(a)), make_float2(F512_R2, F512_R2));
+#else
+  return f2mul(a, make_float2(F512_R2, -F512_R2));
+#endif
+}
+__device__ __forceinline__ float2 f2mul_w8_3(float2 a) {
+#if F512_R2TRICK && F512_PACKED
+  return __fmul2_rn(f2add(a, f2pi(a)), make_float2(-F512_R2, -F512_R2));
+#else
+  return f2mul(a, make_float2(-F512_R2, -F512_R2));
+#endif
+}
+
 // forward 16-point DFT in registers (radix 4x4).  Input v[n]; output X[k] lands in v[4*(k&3) + (k>>2)].
 __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
   // v[4c + b] = y[b][c]; twiddle by W16^(b*c), W16^m = (cos(pi m/8), -sin(pi m/8))
   v[5] = f2mul(v[5], make_float2(F512_C1, -F512_S1));    // W^1
-  v[6] = f2mul(v[6], make_float2(F512_R2, -F512_R2));    // W^2
+  v[6] = f2mul_w8_1(v[6]);                               // W^2
   v[7] = f2mul(v[7], make_float2(F512_S1, -F512_C1));    // W^3
-  v[9] = f2mul(v[9], make_float2(F512_R2, -F512_R2));    // W^2
+  v[9] = f2mul_w8_1(v[9]);                               // W^2
   v[10] = f2mi(v[10]);                                   // W^4 = -i
-  v[11] = f2mul(v[11], make_float2(-F512_R2, -F512_R2)); // W^6
+  v[11] = f2mul_w8_3(v[11]);                             // W^6
   v[13] = f2mul(v[13], make_float2(F512_S1, -F512_C1));  // W^3
-  v[14] = f2mul(v[14], make_float2(-F512_R2, -F512_R2)); // W^6
+  v[14] = f2mul_w8_3(v[14]);                             // W^6
   v[15] = f2mul(v[15], make_float2(-F512_C1, F512_S1));  // W^9
 #pragma unroll
   for (int c = 0; c < 4; ++c) dft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -405,9 +426,19 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         const float sx = l == 0 ? zs0.x : zs.x, sy = l == 0 ? zs0.y : zs.y;
         const float2 cc = f2conj(make_float2(__shfl_sync(F512_FULL, sx, partner, 16), __shfl_sync(F512_FULL, sy, partner, 16)));
         const float2 E = f2add(zk, cc), O = f2sub(zk, cc);
-        float2 wc = w32_const(2 * i);                 // W16^i; lane 0 needs W32^(own slot)
-        if (i >= 5) { const float2 w0 = w32_const(kOwn0[i]); wc = l == 0 ? w0 : wc; }
-        const float2 mit = f2mi(f2mul(f2mul(O, wc), w512l));  // -i*T
+        float2 Ow;                                    // O * W16^i; lane 0 needs W32^(own slot) once i >= 5
+#if F512_R2TRICK
+        if (i == 0) Ow = O;                           // W16^0 = 1, W16^4 = -i, W16^2 = W8^1: no general product needed
+        else if (i == 4) Ow = f2mi(O);
+        else if (i == 2) Ow = f2mul_w8_1(O);
+        else
+#endif
+        {
+          float2 wc = w32_const(2 * i);
+          if (i >= 5) { const float2 w0 = w32_const(kOwn0[i]); wc = l == 0 ? w0 : wc; }
+          Ow = f2mul(O, wc);
+        }
+        const float2 mit = f2mi(f2mul(Ow, w512l));    // -i*T
         const float2 a = f2add(E, mit);               // 2*X[k]
         const float2 bq = f2sub(E, mit);              // 2*conj(X[256-k])
         float pa = fmaf(a.x, a.x, a.y * a.y), pb = fmaf(bq.x, bq.x, bq.y * bq.y);
