@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -275,6 +276,41 @@ class Engine:
         self._check(rc)
         return out, np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
 
+    def extract_host_list(self, arrays: Sequence[np.ndarray], dtype=np.float32, sub_bytes: int = 96 << 20):
+        """A LIST of separately allocated host waveforms -> packed (sum T_i, F) features in pinned host memory + row prefix.
+        The list is cut into sub-batches of ~`sub_bytes`; while the C call (H2D / kernel / D2H pipeline, GIL released)
+        works on sub-batch j out of one pinned staging buffer, the staging threads gather sub-batch j + 1 into the other."""
+        lens = [int(a.shape[0]) for a in arrays]
+        B = len(lens)
+        p = self.plan
+        ns = np.asarray(lens, dtype=np.int64)
+        if p.snip_edges and p.feature != "whisper-fbank":
+            Ts = np.where(ns < p.L, 0, 1 + (ns - p.L) // p.S)
+        else:
+            Ts = (ns + p.S // 2) // p.S
+        prefix = np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
+        out = torch.empty((int(prefix[-1]), self.feature_dim), dtype=torch.float32, pin_memory=True).numpy()
+        esz = 2 if np.dtype(dtype) == np.int16 else 4
+        groups = _groups(lens, sub_bytes, esz)
+        tdt = torch.int16 if esz == 2 else torch.float32
+        cap = max(_aligned_offsets(lens[b0:b1], 4)[1] for b0, b1 in groups)
+        bufs = [torch.empty(cap, dtype=tdt, pin_memory=True) for _ in range(min(2, len(groups)))]
+        stager = (lambda j: stage_host(arrays[groups[j][0]: groups[j][1]], dtype=dtype, out=bufs[j % 2]))
+        cur, nxt = stager(0), None
+        side = ThreadPoolExecutor(max_workers=1) if len(groups) > 1 else None  # drives the staging of j + 1 (fans out to the pool)
+        try:
+            for j, (b0, b1) in enumerate(groups):
+                if side is not None and j + 1 < len(groups):
+                    nxt = side.submit(stager, j + 1)
+                buf, glens, goffs = cur
+                self.extract_host(buf, glens, out=out[prefix[b0]: prefix[b1]], offsets=goffs)
+                if nxt is not None:
+                    cur, nxt = nxt.result(), None
+        finally:
+            if side is not None:
+                side.shutdown(wait=True)
+        return out, prefix
+
     # ------------------------------------------------------------------ introspection
     def get_table(self, which: int) -> np.ndarray:
         cap = max(self.plan.K * max(self.plan.num_filters, 1), self.plan.N * 2, 8192)
@@ -290,44 +326,107 @@ class Engine:
         return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
 
 
-def pack_device(tensors: List[torch.Tensor], device: torch.device, align: int = 4,
-                dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, List[int], List[int]]:
-    """Packs 1-D waveforms into one ragged device buffer (each start aligned to `align` elements).
-    Host tensors go through ONE pinned staging buffer and ONE H2D copy; device tensors are copied
-    device-to-device."""
-    lens = [int(t.numel()) for t in tensors]
+# ---- host staging --------------------------------------------------------------------------------------------------
+# Gathering B separately allocated waveforms into one pinned buffer is a plain memcpy, and ONE host thread moves only a
+# fraction of what PCIe 5 takes (profiles/README.md "list routes"), so the copies are spread over a small thread pool
+# (numpy / torch copies release the GIL) and overlapped with the transfer of the previous group.
+STAGING_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2, int(os.environ.get("B200FEAT_STAGING_THREADS", "8"))))
+_POOL = None
+_POOL_PID = None
+
+
+def _copy_pool() -> Optional[ThreadPoolExecutor]:
+    """Per-process pool (threads do not survive fork(): DataLoader workers get their own on first use)."""
+    global _POOL, _POOL_PID
+    if STAGING_THREADS <= 1:
+        return None
+    if _POOL is None or _POOL_PID != os.getpid():
+        _POOL, _POOL_PID = ThreadPoolExecutor(max_workers=STAGING_THREADS, thread_name_prefix="b200feat-stage"), os.getpid()
+    return _POOL
+
+
+def _groups(lens: Sequence[int], target_bytes: int, esz: int) -> List[Tuple[int, int]]:
+    """Consecutive index ranges [b0, b1) of roughly `target_bytes` each."""
+    out, b0, acc = [], 0, 0
+    for i, n in enumerate(lens):
+        acc += n * esz
+        if acc >= target_bytes:
+            out.append((b0, i + 1))
+            b0, acc = i + 1, 0
+    if b0 < len(lens):
+        out.append((b0, len(lens)))
+    return out
+
+
+def _aligned_offsets(lens: Sequence[int], align: int) -> Tuple[List[int], int]:
     offs, cur = [], 0
     for n in lens:
         cur = (cur + align - 1) // align * align
         offs.append(cur)
         cur += n
-    total = cur
+    return offs, cur
+
+
+def pack_device(tensors: List[torch.Tensor], device: torch.device, align: int = 4,
+                dtype: torch.dtype = torch.float32) -> Tuple[torch.Tensor, List[int], List[int]]:
+    """Packs 1-D waveforms into one ragged device buffer (each start aligned to `align` elements).
+    Host tensors are gathered into ONE pinned staging buffer by the staging threads, group by group, and every finished
+    group is sent to the device at once (its H2D copy overlaps the gathering of the next group); device tensors are
+    copied device-to-device."""
+    lens = [int(t.numel()) for t in tensors]
+    offs, total = _aligned_offsets(lens, align)
     if all(not t.is_cuda for t in tensors):
-        stage = torch.empty(total, dtype=dtype, pin_memory=torch.cuda.is_available())
-        for t, o, n in zip(tensors, offs, lens):
-            stage[o:o + n].copy_(t.reshape(-1))
-        return stage.to(device, non_blocking=True), lens, offs
+        cuda = torch.cuda.is_available()
+        stage = torch.empty(total, dtype=dtype, pin_memory=cuda)
+        pool = _copy_pool()
+        esz = stage.element_size()
+
+        def gather(b0, b1):
+            for i in range(b0, b1):
+                if i > 0:
+                    stage[offs[i - 1] + lens[i - 1]: offs[i]] = 0  # alignment gap: defined bytes only
+                stage[offs[i]: offs[i] + lens[i]].copy_(tensors[i].reshape(-1))
+
+        if pool is None or total * esz < (8 << 20) or not cuda:
+            gather(0, len(tensors))
+            return stage.to(device, non_blocking=True), lens, offs
+        dev = torch.empty(total, dtype=dtype, device=device)
+        groups = _groups(lens, max(4 << 20, total * esz // (4 * STAGING_THREADS)), esz)
+        futs = [pool.submit(gather, b0, b1) for b0, b1 in groups]
+        for (b0, b1), f in zip(groups, futs):
+            f.result()
+            e0, e1 = offs[b0], offs[b1 - 1] + lens[b1 - 1]
+            dev[e0:e1].copy_(stage[e0:e1], non_blocking=True)
+        return dev, lens, offs
     buf = torch.empty(total, dtype=dtype, device=device)
     for t, o, n in zip(tensors, offs, lens):
         buf[o:o + n].copy_(t.reshape(-1), non_blocking=True)
     return buf, lens, offs
 
 
-def stage_host(arrays: Sequence[np.ndarray], dtype=np.float32, align: int = 4) -> Tuple[torch.Tensor, List[int], List[int]]:
-    """Copies 1-D host waveforms into ONE pinned buffer, each start aligned to `align` elements (gaps are zero-filled so
-    that no uninitialised memory crosses PCIe).  Returns (buffer, lengths, offsets) for `Engine.extract_host(offsets=)`."""
+def stage_host(arrays: Sequence[np.ndarray], dtype=np.float32, align: int = 4,
+               out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, List[int], List[int]]:
+    """Copies 1-D host waveforms into ONE pinned buffer (`out`, or a fresh one), each start aligned to `align` elements
+    (gaps are zero-filled so that no uninitialised memory crosses PCIe), using the staging threads.
+    Returns (buffer, lengths, offsets) for `Engine.extract_host(offsets=)`."""
     lens = [int(a.shape[0]) for a in arrays]
-    offs, cur = [], 0
-    for n in lens:
-        cur = (cur + align - 1) // align * align
-        offs.append(cur)
-        cur += n
+    offs, cur = _aligned_offsets(lens, align)
     tdt = torch.int16 if np.dtype(dtype) == np.int16 else torch.float32
-    stage = torch.empty(max(cur, 1), dtype=tdt, pin_memory=torch.cuda.is_available())
+    stage = out if out is not None else torch.empty(max(cur, 1), dtype=tdt, pin_memory=torch.cuda.is_available())
+    assert stage.dtype == tdt and stage.numel() >= cur
     view = stage.numpy()
-    prev_end = 0
-    for a, o, n in zip(arrays, offs, lens):
-        view[prev_end:o] = 0
-        view[o:o + n] = a
-        prev_end = o + n
-    return stage, lens, offs
+
+    def gather(b0, b1):
+        for i in range(b0, b1):
+            if i > 0:
+                view[offs[i - 1] + lens[i - 1]: offs[i]] = 0
+            view[offs[i]: offs[i] + lens[i]] = arrays[i]
+
+    pool = _copy_pool()
+    esz = 2 if tdt == torch.int16 else 4
+    if pool is None or cur * esz < (8 << 20):
+        gather(0, len(arrays))
+    else:
+        for f in [pool.submit(gather, b0, b1) for b0, b1 in _groups(lens, max(4 << 20, cur * esz // (2 * STAGING_THREADS)), esz)]:
+            f.result()
+    return stage[:max(cur, 1)], lens, offs

@@ -316,9 +316,14 @@ class _B200Extractor(FeatureExtractor):
             else:
                 flat = [np.asarray(x).squeeze() for x in items]
                 dt = np.int16 if all(a.dtype == np.int16 for a in flat) else np.float32
-                # one pinned staging buffer, every cut on a 4-element boundary (vector-load path of the kernels)
-                stage, lens, offs = stage_host(flat, dtype=dt)
-                out, prefix = eng.extract_host(stage, lens, offsets=offs)
+                # pinned staging with every cut on a 4-element boundary (vector-load path of the kernels), gathered by the
+                # staging threads and double-buffered against the H2D / kernel / D2H pipeline of the C call
+                lens = [int(a.shape[0]) for a in flat]
+                if hasattr(eng, "extract_host_list"):
+                    out, prefix = eng.extract_host_list(flat, dtype=dt)
+                else:
+                    stage, lens, offs = stage_host(flat, dtype=dt)
+                    out, prefix = eng.extract_host(stage, lens, offsets=offs)
             result = [out[prefix[i]: prefix[i + 1]] for i in range(len(lens))]
         if self._returns_cpu_tensor and input_is_torch:
             result = [r.cpu() for r in result]
