@@ -276,7 +276,7 @@ class Engine:
         self._check(rc)
         return out, np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
 
-    def extract_host_list(self, arrays: Sequence[np.ndarray], dtype=np.float32, sub_bytes: int = 96 << 20):
+    def extract_host_list(self, arrays: Sequence[np.ndarray], dtype=np.float32, sub_bytes: int = 64 << 20):
         """A LIST of separately allocated host waveforms -> packed (sum T_i, F) features in pinned host memory + row prefix.
         The list is cut into sub-batches of ~`sub_bytes`; while the C call (H2D / kernel / D2H pipeline, GIL released)
         works on sub-batch j out of one pinned staging buffer, the staging threads gather sub-batch j + 1 into the other."""
@@ -291,7 +291,7 @@ class Engine:
         prefix = np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
         out = torch.empty((int(prefix[-1]), self.feature_dim), dtype=torch.float32, pin_memory=True).numpy()
         esz = 2 if np.dtype(dtype) == np.int16 else 4
-        groups = _groups(lens, sub_bytes, esz)
+        groups = _groups(lens, sub_bytes, esz, ramp=True)
         tdt = torch.int16 if esz == 2 else torch.float32
         cap = max(_aligned_offsets(lens[b0:b1], 4)[1] for b0, b1 in groups)
         bufs = [torch.empty(cap, dtype=tdt, pin_memory=True) for _ in range(min(2, len(groups)))]
@@ -345,12 +345,13 @@ def _copy_pool() -> Optional[ThreadPoolExecutor]:
     return _POOL
 
 
-def _groups(lens: Sequence[int], target_bytes: int, esz: int) -> List[Tuple[int, int]]:
-    """Consecutive index ranges [b0, b1) of roughly `target_bytes` each."""
+def _groups(lens: Sequence[int], target_bytes: int, esz: int, ramp: bool = False) -> List[Tuple[int, int]]:
+    """Consecutive index ranges [b0, b1) of roughly `target_bytes` each; with `ramp` the first two groups are 1/4 and 1/2
+    of that (a software pipeline starts sooner on a small first stage)."""
     out, b0, acc = [], 0, 0
     for i, n in enumerate(lens):
         acc += n * esz
-        if acc >= target_bytes:
+        if acc >= (target_bytes >> max(0, 2 - len(out)) if ramp else target_bytes):
             out.append((b0, i + 1))
             b0, acc = i + 1, 0
     if b0 < len(lens):
@@ -381,11 +382,17 @@ def pack_device(tensors: List[torch.Tensor], device: torch.device, align: int = 
         pool = _copy_pool()
         esz = stage.element_size()
 
+        view = stage.numpy()
+
         def gather(b0, b1):
             for i in range(b0, b1):
                 if i > 0:
-                    stage[offs[i - 1] + lens[i - 1]: offs[i]] = 0  # alignment gap: defined bytes only
-                stage[offs[i]: offs[i] + lens[i]].copy_(tensors[i].reshape(-1))
+                    view[offs[i - 1] + lens[i - 1]: offs[i]] = 0  # alignment gap: defined bytes only
+                t = tensors[i]
+                if t.requires_grad or not t.is_contiguous():
+                    stage[offs[i]: offs[i] + lens[i]].copy_(t.detach().reshape(-1))
+                else:  # a numpy view of the tensor: plain memcpy (3x torch's CPU copy_ on this path), GIL released
+                    view[offs[i]: offs[i] + lens[i]] = t.numpy().reshape(-1)
 
         if pool is None or total * esz < (8 << 20) or not cuda:
             gather(0, len(tensors))

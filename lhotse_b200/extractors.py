@@ -290,7 +290,12 @@ class _B200Extractor(FeatureExtractor):
             if arr.dtype not in (np.float32, np.int16):
                 arr = arr.astype(np.float32)
             lens = [nmax] * B
-            out, prefix = eng.extract_host(arr.reshape(-1), lens)
+            if arr.nbytes >= (16 << 20) and hasattr(eng, "extract_host_list") and not torch.from_numpy(arr).is_pinned():
+                # pageable memory: the driver would bounce it through its own staging on ONE thread; gather the rows into
+                # pinned memory with the staging threads instead, double-buffered against the transfer
+                out, prefix = eng.extract_host_list(list(arr), dtype=arr.dtype)
+            else:
+                out, prefix = eng.extract_host(arr.reshape(-1), lens)
             result = [out[prefix[i]: prefix[i + 1]] for i in range(B)]
             input_is_torch = False
         else:

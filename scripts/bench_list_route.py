@@ -56,7 +56,11 @@ def main():
             E.STAGING_THREADS = keep
 
     print(json.dumps({"staging_threads": E.STAGING_THREADS, "cpu_count": os.cpu_count()}), flush=True)
+    pageable = arr.copy()
+    eng = ext.engine
     for name, fn in (("(B, n) pinned array (bench.py e2e)", lambda: ext.extract_batch(arr, SR)),
+                     ("(B, n) pageable array handed to the C call as is (before)", lambda: eng.extract_host(pageable.reshape(-1), [n] * B)),
+                     ("(B, n) pageable array", lambda: ext.extract_batch(pageable, SR)),
                      ("list of numpy arrays, single-thread staging then C call (before)", legacy_numpy),
                      ("list of CPU torch tensors -> padded device tensor, single-thread staging (before)", legacy_torch),
                      ("list of numpy arrays", lambda: ext.extract_batch(lst, SR)),
