@@ -12,6 +12,7 @@
  *   - lhotse/features/kaldi/extractors.py:407 LogSpectrogram (.extract :428)
  *   - lhotse/features/kaldi/extractors.py:485 _extract_batch (pad, forward, trim)
  *   - lhotse/features/whisper_fbank.py:16-84  log_mel_spectrogram, :103 WhisperFbank (.extract :138)
+ *   - lhotse/features/librosa_fbank.py:64-135 logmelfilterbank, :139 LibrosaFbank (.extract :157)
  *   - lhotse/features/kaldi/layers.py:151-186, :309-320, :392-402, :461-473, :565-578, :708-724
  *     (the arithmetic), :727-772 (framing), lhotse/utils.py:424-434 (frame-count contract)
  *
@@ -57,6 +58,10 @@ extern "C" {
                                       maximum - 8, (x + 4) / 4; rows beyond the stft's n/S frames are 0 (:73-80).
                                       Two launches per batch: the fused kernel (+ per-cut max) and a normalise pass. */
 
+#define B200FEAT_LOG10_FBANK 5     /* LibrosaFbank / logmelfilterbank, lhotse/features/librosa_fbank.py:64-135: centred STFT
+                                      (librosa.stft, pad_mode="reflect"), |X| (use_fft_mag) or |X|^2, mel, log10(max(., mel_floor));
+                                      rows = compute_num_frames (:128-134).  One launch, any fast kernel. */
+
 /* sample dtypes accepted by the kernels */
 #define B200FEAT_F32 0 /* float32 in [-1, 1] — what lhotse hands to extract() */
 #define B200FEAT_I16 1 /* int16 PCM; converted as x/32768 on load (libsndfile convention) */
@@ -98,7 +103,7 @@ typedef struct b200feat_plan_desc {
   int32_t energy_style; /* B200FEAT_ENERGY_* */
   int32_t use_lifter;   /* multiply cepstra by lifter[] */
   int32_t kernel;       /* B200FEAT_KERNEL_* */
-  int32_t pad_mode;     /* B200FEAT_PAD_* (B200FEAT_PAD_CENTER is accepted with B200FEAT_WHISPER_FBANK only) */
+  int32_t pad_mode;     /* B200FEAT_PAD_* (B200FEAT_PAD_CENTER goes with B200FEAT_WHISPER_FBANK and B200FEAT_LOG10_FBANK) */
   float preemph_coeff;  /* 0 disables, layers.py:165 */
   float energy_floor;   /* linear-domain floor (EPSILON = 1e-10 by default) */
   float mel_floor;      /* clamp before log for fbank/mfcc: finfo(float32).eps, layers.py:572 */
@@ -147,7 +152,7 @@ const char *b200feat_last_error(const b200feat_handle *h);
 /* T for a cut of n samples (layers.py:747-753); B200FEAT_ESHORT if it cannot be framed
  * (n too short for a single reflection — the reference raises on those). */
 int64_t b200feat_num_frames(const b200feat_handle *h, int64_t num_samples);
-/* F: M (+1 with use_energy) for fbank, M for whisper-fbank, C for mfcc, N/2+1 for the spectrogram kinds. */
+/* F: M (+1 with use_energy) for fbank, M for whisper-fbank / log10-fbank, C for mfcc, N/2+1 for the spectrogram kinds. */
 int32_t b200feat_feature_dim(const b200feat_handle *h);
 /* B200FEAT_KERNEL_GENERIC or B200FEAT_KERNEL_FAST — what AUTO resolved to. */
 int32_t b200feat_kernel_kind(const b200feat_handle *h);

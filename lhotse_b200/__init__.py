@@ -4,6 +4,8 @@ from .plan import EPSILON, LOG_EPSILON, FeaturePlan, build_plan  # noqa: F401
 from .extractors import (  # noqa: F401
     B200Fbank,
     B200FbankConfig,
+    B200LibrosaFbank,
+    B200LibrosaFbankConfig,
     B200LogSpectrogram,
     B200LogSpectrogramConfig,
     B200Mfcc,

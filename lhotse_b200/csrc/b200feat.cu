@@ -96,6 +96,7 @@ std::vector<int> factorize(int n) {
 int64_t frames_for(const b200feat_plan_desc &d, int64_t n) {
   const int64_t L = d.frame_length, S = d.frame_shift;
   if (d.feature == B200FEAT_WHISPER_FBANK) return (n + S / 2) / S;
+  if (d.feature == B200FEAT_LOG10_FBANK && d.pad_mode == B200FEAT_PAD_CENTER) return (n + S / 2) / S;  // librosa_fbank.py:128-134
   if (d.snip_edges) return n < L ? 0 : 1 + (n - L) / S;
   return (n + S / 2) / S;
 }
@@ -128,12 +129,17 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   if (L <= 0 || S <= 0 || N < L || N < 2) return fail(nullptr, B200FEAT_EINVAL, "bad L/S/N");
   if (!window) return fail(nullptr, B200FEAT_EINVAL, "window table is required");
   const bool whisper = desc->feature == B200FEAT_WHISPER_FBANK;
-  const bool mel = desc->feature == B200FEAT_FBANK || desc->feature == B200FEAT_MFCC || whisper;
-  if (desc->feature < 0 || desc->feature > 4) return fail(nullptr, B200FEAT_EINVAL, "bad feature kind");
+  const bool log10fb = desc->feature == B200FEAT_LOG10_FBANK;
+  const bool mel = desc->feature == B200FEAT_FBANK || desc->feature == B200FEAT_MFCC || whisper || log10fb;
+  if (desc->feature < 0 || desc->feature > 5) return fail(nullptr, B200FEAT_EINVAL, "bad feature kind");
   if (desc->pad_mode != B200FEAT_PAD_KALDI && desc->pad_mode != B200FEAT_PAD_CENTER)
     return fail(nullptr, B200FEAT_EINVAL, "bad pad_mode");
-  if ((desc->pad_mode == B200FEAT_PAD_CENTER) != whisper)
-    return fail(nullptr, B200FEAT_EINVAL, "pad_mode CENTER goes with the whisper-fbank kind (and only with it)");
+  if (whisper && desc->pad_mode != B200FEAT_PAD_CENTER)
+    return fail(nullptr, B200FEAT_EINVAL, "whisper-fbank needs pad_mode CENTER");
+  if (desc->pad_mode == B200FEAT_PAD_CENTER && !(whisper || log10fb))
+    return fail(nullptr, B200FEAT_EINVAL, "pad_mode CENTER goes with the whisper-fbank and log10-fbank kinds only");
+  if (log10fb && (desc->use_energy || desc->mel_floor <= 0.f || (desc->pad_mode == B200FEAT_PAD_CENTER && desc->snip_edges)))
+    return fail(nullptr, B200FEAT_EINVAL, "log10-fbank: use_energy must be off, mel_floor > 0, no snip_edges with CENTER");
   if (whisper && (desc->snip_edges || desc->use_energy || desc->use_fft_mag || desc->mel_floor <= 0.f))
     return fail(nullptr, B200FEAT_EINVAL, "whisper-fbank: snip_edges / use_energy / use_fft_mag must be off, mel_floor > 0");
   if (mel && (desc->num_filters <= 0 || !mel_bank)) return fail(nullptr, B200FEAT_EINVAL, "mel bank required");
@@ -170,6 +176,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   p.Nc = p.packed ? N / 2 : N;
   p.pad_mode = desc->pad_mode;
   p.whisper = whisper ? 1 : 0;
+  p.log10_mel = (whisper || log10fb) ? 1 : 0;
   p.pad_left = desc->pad_mode == B200FEAT_PAD_CENTER ? N / 2 : (L - S) / 2;
   p.snip_edges = desc->snip_edges; p.remove_dc = desc->remove_dc_offset;
   p.use_energy = desc->use_energy; p.raw_energy = desc->raw_energy; p.use_mag = desc->use_fft_mag;
@@ -185,6 +192,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   switch (desc->feature) {
     case B200FEAT_FBANK: p.F = p.M + (desc->use_energy ? 1 : 0); break;
     case B200FEAT_WHISPER_FBANK: p.F = p.M; break;
+    case B200FEAT_LOG10_FBANK: p.F = p.M; break;
     case B200FEAT_MFCC: p.F = p.C; break;
     default: p.F = p.K;
   }
@@ -241,6 +249,11 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
 
   // ---- kernel selection
   // the whisper-fbank epilogue / centre padding exist in the generic and the fast400 kernels only
+  // (fast512x2 has neither centre padding nor the log10 epilogue; it is an explicit, experimental choice anyway)
+  if (desc->kernel == B200FEAT_KERNEL_FAST_X2 && (whisper || log10fb)) {
+    cudaSetDevice(prev); b200feat_destroy(h);
+    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast_x2 supports the Kaldi kinds only");
+  }
   const bool fast512_ok = !whisper && fastx2_supported(p) && fast512_supported(p);
   const bool fast256_ok = !whisper && fast256_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
   const bool fast1024_ok = !whisper && fast1024_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;

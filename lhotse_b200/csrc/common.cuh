@@ -17,7 +17,8 @@ struct DevPlan {
   int packed;                        // 1 if even N
   int pad_left;                      // (L - S) / 2 when !snip_edges (B200FEAT_PAD_KALDI); N / 2 with B200FEAT_PAD_CENTER
   int pad_mode;                      // B200FEAT_PAD_*: 0 mirrors with the edge sample, 1 without (torch "reflect")
-  int whisper;                       // feature == B200FEAT_WHISPER_FBANK: log10 epilogue + per-cut max, n / S valid frames
+  int whisper;                       // feature == B200FEAT_WHISPER_FBANK: per-cut max + normalise pass, n / S valid frames
+  int log10_mel;                     // mel epilogue in log10 (whisper-fbank, librosa-fbank) instead of ln
   int snip_edges, remove_dc, use_energy, raw_energy, use_mag, energy_style, use_lifter;
   int nstages;
   int radix[B200_MAX_STAGES];

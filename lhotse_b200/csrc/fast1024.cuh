@@ -158,12 +158,12 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           v[n1] = pv[n1] = make_float2(0.f, 0.f);
           if (ja < L) {
             int64_t i = base + ja;
-            if (!p.snip_edges) i = reflect_index(i, n);
+            if (!p.snip_edges) i = reflect_index(i, n, p.pad_mode);
             v[n1].x = ld_sample<DT>(b.samples, xoff + i);
           }
           if (ja + 2 < L) {
             int64_t i = base + ja + 2;
-            if (!p.snip_edges) i = reflect_index(i, n);
+            if (!p.snip_edges) i = reflect_index(i, n, p.pad_mode);
             v[n1].y = ld_sample<DT>(b.samples, xoff + i);
           }
         }
@@ -282,6 +282,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
       }
     } else {
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      const float lgk = p.log10_mel ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (librosa_fbank.py:126) or ln
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(xall + (size_t)(2 * w) * F512_XBUF);  // both transpose tiles of the warp
       for (int j = 0; j < ft.mel_rounds; ++j) {
@@ -306,8 +307,8 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         if (m < p.M) {
           float r[SLOTS];
 #pragma unroll
-          for (int f = 0; f < SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[f], p.mel_floor));
-          if (p.feature == B200FEAT_FBANK) {
+          for (int f = 0; f < SLOTS; ++f) r[f] = fast_lg2_normal(nanmax(acc[f], p.mel_floor)) * lgk;
+          if (p.feature != B200FEAT_MFCC) {
             float *orow = out + m + shift;
 #pragma unroll
             for (int f = 0; f < SLOTS; ++f)
@@ -325,7 +326,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           for (int f = 0; f < SLOTS; ++f) v0 = (lane == f) ? le[f] : v0;
           out[(int64_t)lane * p.F] = v0;
         }
-      } else {
+      } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int idx = lane; idx < nvalid * p.C; idx += 32) {
           const int f = idx / p.C, c = idx - f * p.C;

@@ -296,7 +296,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(X);  // the exchange tile is idle during the epilogue
-      const float lgk = p.whisper ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (whisper_fbank.py:67) or ln
+      const float lgk = p.log10_mel ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (whisper_fbank.py:67) or ln
       float vmax = __int_as_float(0xff800000);
       // rounds of 16 filters, two per lane (l and l + 8): the per-round overhead is shared by 2 filters x 2 frames
       for (int j = 0; j < ft.mel_rounds; ++j) {
@@ -349,7 +349,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
           for (int f = 0; f < F400_SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
           out[(int64_t)l * p.F] = v0;
         }
-      } else {
+      } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int idx = l; idx < nvalid * p.C; idx += 8) {
           const int f = idx / p.C, c = idx - f * p.C;

@@ -328,17 +328,17 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           float a = 0.f, c = 0.f, pr = 0.f;
           if (j0 < L) {
             int64_t i = base + j0;
-            if (!p.snip_edges) i = reflect_index(i, n);
+            if (!p.snip_edges) i = reflect_index(i, n, p.pad_mode);
             a = ld_sample<DT>(b.samples, xoff + i);
             if (!F512_PREV_SHFL) {
               int64_t ip = base + (j0 > 0 ? j0 - 1 : 0);
-              if (!p.snip_edges) ip = reflect_index(ip, n);
+              if (!p.snip_edges) ip = reflect_index(ip, n, p.pad_mode);
               pr = ld_sample<DT>(b.samples, xoff + ip);
             }
           }
           if (j0 + 1 < L) {
             int64_t i = base + j0 + 1;
-            if (!p.snip_edges) i = reflect_index(i, n);
+            if (!p.snip_edges) i = reflect_index(i, n, p.pad_mode);
             c = ld_sample<DT>(b.samples, xoff + i);
           }
           v[n1] = make_float2(a, c);
@@ -480,6 +480,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
       }
     } else {
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      const float lgk = p.log10_mel ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (librosa_fbank.py:126) or ln
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(X);  // the transpose tile is idle during the epilogue
       for (int j = 0; j < ft.mel_rounds; ++j) {
@@ -502,8 +503,8 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         if (m < p.M) {
           float r[SLOTS];
 #pragma unroll
-          for (int f = 0; f < SLOTS; ++f) r[f] = fast_log_normal(nanmax(acc[f], p.mel_floor));
-          if (p.feature == B200FEAT_FBANK) {
+          for (int f = 0; f < SLOTS; ++f) r[f] = fast_lg2_normal(nanmax(acc[f], p.mel_floor)) * lgk;
+          if (p.feature != B200FEAT_MFCC) {
             float *orow = out + m + shift;
             if (nvalid == SLOTS) {  // the common case: no per-row guards
 #pragma unroll
@@ -524,7 +525,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
           out[(int64_t)l * p.F] = v0; }
-      } else {
+      } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int idx = l; idx < nvalid * p.C; idx += 16) {
           const int f = idx / p.C, c = idx - f * p.C;

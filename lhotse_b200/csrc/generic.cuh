@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         float acc = 0.f;
         for (int i = 0; i < len; ++i) acc += raw[st + i] * __ldg(w + i);
         const float fl = nanmax(acc, p.mel_floor);
-        const float v = p.whisper ? log10f(fl) : logf(fl);  // whisper_fbank.py:67
+        const float v = p.log10_mel ? log10f(fl) : logf(fl);  // whisper_fbank.py:67, librosa_fbank.py:126
         vmax = nanmax(vmax, v);
         if (p.feature == B200FEAT_MFCC) mlog[m] = v; else out[m + shift] = v;
       }
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         if (lane == 0 && t < n / p.S) atomic_max_float(b.cut_max + cut, vmax);
       } else if (p.feature == B200FEAT_FBANK) {
         if (shift && lane == 0) out[0] = le;
-      } else {
+      } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int c = lane; c < p.C; c += 32) {
           float acc = 0.f;

@@ -258,7 +258,7 @@ class Engine:
         assert (int(ns.sum()) if off is None else int(off[-1] + ns[-1])) <= numel
         B = len(ns)
         p = self.plan
-        if p.snip_edges and p.feature != "whisper-fbank":
+        if p.snip_edges and p.feature not in ("whisper-fbank", "librosa-fbank"):
             Ts = np.where(ns < p.L, 0, 1 + (ns - p.L) // p.S)
         else:
             Ts = (ns + p.S // 2) // p.S
@@ -284,7 +284,7 @@ class Engine:
         B = len(lens)
         p = self.plan
         ns = np.asarray(lens, dtype=np.int64)
-        if p.snip_edges and p.feature != "whisper-fbank":
+        if p.snip_edges and p.feature not in ("whisper-fbank", "librosa-fbank"):
             Ts = np.where(ns < p.L, 0, 1 + (ns - p.L) // p.S)
         else:
             Ts = (ns + p.S // 2) // p.S

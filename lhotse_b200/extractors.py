@@ -9,6 +9,7 @@ B200-native counterparts of lhotse's Kaldi-family extractors, behind the unchang
     Spectrogram     :297  name "kaldi-spectrogram"             B200Spectrogram     "b200-spectrogram"
     LogSpectrogram  :407  name "kaldi-log-spectrogram"         B200LogSpectrogram  "b200-log-spectrogram"
     WhisperFbank (lhotse/features/whisper_fbank.py:103)  "whisper-fbank"    B200WhisperFbank    "b200-whisper-fbank"
+    LibrosaFbank (lhotse/features/librosa_fbank.py:139)  "librosa-fbank"    B200LibrosaFbank    "b200-librosa-fbank"
 
 Same config fields, same container rules for ``extract`` / ``extract_batch``
 (extractors.py:92-132, :485-554), same ``mix`` / ``compute_energy`` / ``scale`` statics.
@@ -551,7 +552,65 @@ class B200WhisperFbank(_B200Extractor):
     scale = staticmethod(B200Fbank.scale)
 
 
+@dataclass
+class B200LibrosaFbankConfig:
+    """Field-for-field LibrosaFbankConfig (librosa_fbank.py:16-38) + device / kernel."""
+
+    sampling_rate: int = 22050
+    fft_size: int = 1024
+    hop_size: int = 256
+    win_length: Optional[int] = None
+    window: str = "hann"
+    num_mel_bins: int = 80
+    fmin: Optional[int] = 80
+    fmax: Optional[int] = 7600
+    device: str = "cuda"
+    kernel: str = "auto"
+
+    dither = 0.0        # not dataclass fields: the reference has no such knobs
+    snip_edges = False
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any]):
+        return cls(**data)
+
+
+@register_extractor
+class B200LibrosaFbank(_B200Extractor):
+    """`LibrosaFbank` (librosa_fbank.py:139-184; the TTS-style log-mel of ParallelWaveGAN & co): centred STFT with a periodic
+    window, magnitudes, Slaney mel filters between fmin and fmax, log10 — one launch of the fused kernel for the plan's
+    fft_size (register-resident for 256 / 400 / 512 / 1024, generic otherwise).  librosa itself (an unpinned optional
+    dependency of the reference, absent here) is restated; see oracle/librosa_oracle.py for how that is pinned."""
+
+    name = "b200-librosa-fbank"
+    config_type = B200LibrosaFbankConfig
+    feature_kind = "librosa-fbank"
+
+    @property
+    def frame_shift(self) -> Seconds:
+        return self.config.hop_size / self.config.sampling_rate  # librosa_fbank.py:149-151
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self.config.num_mel_bins
+
+    def extract(self, samples: ArrayLike, sampling_rate: int) -> ArrayLike:
+        if samples.ndim == 2:  # librosa_fbank.py:101-105
+            assert samples.shape[0] == 1, f"LibrosaFbank works only with single-channel recordings (shape: {samples.shape})"
+        return super().extract(samples, sampling_rate)
+
+    def online_inference(self, samples, context=None):
+        raise NotImplementedError("LibrosaFbank has no streaming mode in the reference")
+
+    mix = staticmethod(B200Fbank.mix)
+    compute_energy = staticmethod(B200Fbank.compute_energy)
+    scale = staticmethod(B200Fbank.scale)
+
+
 _ALIASES = {
+    "librosa-fbank": B200LibrosaFbank,
     "kaldi-fbank": B200Fbank, "kaldi-mfcc": B200Mfcc,
     "kaldi-spectrogram": B200Spectrogram, "kaldi-log-spectrogram": B200LogSpectrogram,
     "whisper-fbank": B200WhisperFbank,

@@ -20,7 +20,7 @@ import torch
 EPSILON = 1e-10  # lhotse/utils.py:50
 LOG_EPSILON = math.log(EPSILON)  # lhotse/utils.py:51 — the collation pad value
 
-FEATURE_KINDS = {"fbank": 0, "mfcc": 1, "spectrogram": 2, "log-spectrogram": 3, "whisper-fbank": 4}
+FEATURE_KINDS = {"fbank": 0, "mfcc": 1, "spectrogram": 2, "log-spectrogram": 3, "whisper-fbank": 4, "librosa-fbank": 5}
 ENERGY_LHOTSE, ENERGY_KALDI = 0, 1
 PAD_KALDI, PAD_CENTER = 0, 1  # include/b200feat.h B200FEAT_PAD_*
 WINDOWS = ("hamming", "hanning", "povey", "rectangular", "blackman")
@@ -203,7 +203,7 @@ class FeaturePlan:
     def feature_dim(self) -> int:
         if self.feature == "fbank":
             return self.num_filters + (1 if self.use_energy else 0)
-        if self.feature == "whisper-fbank":
+        if self.feature in ("whisper-fbank", "librosa-fbank"):
             return self.num_filters
         if self.feature == "mfcc":
             return self.num_ceps
@@ -211,7 +211,7 @@ class FeaturePlan:
 
     def num_frames(self, n: int) -> int:
         """layers.py:747-753 (the in-layer twin of utils.py:424-434); whisper-fbank: whisper_fbank.py:73-80."""
-        if self.snip_edges and self.feature != "whisper-fbank":
+        if self.snip_edges and self.feature not in ("whisper-fbank", "librosa-fbank"):
             return 0 if n < self.L else 1 + (n - self.L) // self.S
         return (n + self.S // 2) // self.S
 
@@ -254,6 +254,8 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
         raise ValueError(f"unknown feature kind {feature}")
     if feature == "whisper-fbank":
         return build_whisper_plan(cfg)
+    if feature == "librosa-fbank":
+        return build_librosa_plan(cfg)
     frame = _get(cfg, "frame_opts", default=cfg)  # kaldifeat nests the frame options
     melo = _get(cfg, "mel_opts", default=cfg)
     compat = getattr(cfg, "compat", "lhotse")  # our configs carry the family explicitly
@@ -343,4 +345,54 @@ def build_whisper_plan(cfg: Any) -> FeaturePlan:
     )
     plan.window = torch.hann_window(n_fft).to(torch.float32).numpy().copy()  # whisper_fbank.py:116 (periodic)
     plan.mel_bank = make_slaney_mel_bank(sr, n_fft, M)
+    return plan
+
+
+def make_periodic_window(name: str, length: int) -> np.ndarray:
+    """scipy.signal.get_window(name, length, fftbins=True) — what librosa.stft builds (float64) — for the cosine-sum
+    windows, rounded once to float32."""
+    k = np.arange(length, dtype=np.float64)
+    a = 2.0 * np.pi * k / length
+    if name in ("hann", "hanning"):
+        w = 0.5 - 0.5 * np.cos(a)
+    elif name == "hamming":
+        w = 0.54 - 0.46 * np.cos(a)
+    elif name == "blackman":
+        w = 0.42 - 0.5 * np.cos(a) + 0.08 * np.cos(2 * a)
+    elif name in ("boxcar", "rectangular", "ones"):
+        w = np.ones(length)
+    else:
+        raise ValueError(f"unsupported librosa window {name!r} (hann, hamming, blackman, boxcar)")
+    return w.astype(np.float32)
+
+
+def build_librosa_plan(cfg: Any) -> FeaturePlan:
+    """LibrosaFbankConfig (librosa_fbank.py:16-38: sampling_rate, fft_size, hop_size, win_length, window, num_mel_bins,
+    fmin, fmax) -> plan for `logmelfilterbank` (:64-135): librosa.stft(n_fft, hop_length, win_length, window,
+    pad_mode="reflect") = centred frames of n_fft samples under a periodic window of win_length centred in the frame;
+    |X| (magnitudes, :117); librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) (Slaney); log10(max(1e-10, .)) (:126);
+    rows = compute_num_frames(len / sr, hop / sr, sr) (:128-134: the stft's 1 + n // hop frames, minus the last one when
+    n mod hop < hop / 2)."""
+    sr = int(_get(cfg, "sampling_rate", default=22050))
+    N = int(_get(cfg, "fft_size", default=1024))
+    S = int(_get(cfg, "hop_size", default=256))
+    wl = _get(cfg, "win_length", default=None)
+    wl = N if wl is None else int(wl)
+    M = int(_get(cfg, "num_mel_bins", default=80))
+    if N < 2 or N % 2 or S < 1 or not (0 < wl <= N) or M < 1:
+        raise ValueError(f"degenerate librosa geometry fft_size={N} hop_size={S} win_length={wl} num_mel_bins={M}")
+    fmin = _get(cfg, "fmin", default=80)
+    fmax = _get(cfg, "fmax", default=7600)
+    fmin = 0.0 if fmin is None else float(fmin)
+    fmax = sr / 2 if fmax is None else float(fmax)
+    plan = FeaturePlan(
+        feature="librosa-fbank", sampling_rate=sr, L=N, S=S, N=N, num_filters=M,
+        snip_edges=False, remove_dc_offset=False, use_energy=False, raw_energy=True, use_fft_mag=True,
+        preemph_coeff=0.0, mel_floor=EPSILON, pad_mode=PAD_CENTER,
+    )
+    win = np.zeros(N, dtype=np.float32)
+    lo = (N - wl) // 2  # librosa.util.pad_center
+    win[lo: lo + wl] = make_periodic_window(str(_get(cfg, "window", default="hann")), wl)
+    plan.window = win
+    plan.mel_bank = make_slaney_mel_bank(sr, N, M, fmin=fmin, fmax=fmax)
     return plan
