@@ -381,8 +381,8 @@ def build_librosa_plan(cfg: Any) -> FeaturePlan:
     M = int(_get(cfg, "num_mel_bins", default=80))
     if N < 2 or N % 2 or S < 1 or not (0 < wl <= N) or M < 1:
         raise ValueError(f"degenerate librosa geometry fft_size={N} hop_size={S} win_length={wl} num_mel_bins={M}")
-    fmin = _get(cfg, "fmin", default=80)
-    fmax = _get(cfg, "fmax", default=7600)
+    fmin = getattr(cfg, "fmin", 80)   # None is meaningful here (librosa_fbank.py:119-120): 0 Hz / Nyquist
+    fmax = getattr(cfg, "fmax", 7600)
     fmin = 0.0 if fmin is None else float(fmin)
     fmax = sr / 2 if fmax is None else float(fmax)
     plan = FeaturePlan(

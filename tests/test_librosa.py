@@ -105,6 +105,13 @@ def test_librosa_plan_and_config_contract():
     assert type(ext).from_dict(dict(d)).config.to_dict() == ext.config.to_dict()
     q = build_plan("librosa-fbank", B200LibrosaFbankConfig(win_length=800))  # window centred in the frame (pad_center)
     assert np.all(q.window[:112] == 0) and np.all(q.window[912:] == 0) and q.window[112 + 400] == pytest.approx(1.0)
+    # fmin / fmax = None mean 0 Hz / Nyquist (librosa_fbank.py:119-120), not "use the default"
+    for i, c, _, _ in GOLD:
+        cfg = c["cfg"]
+        pl = build_plan("librosa-fbank", B200LibrosaFbankConfig(**cfg))
+        fmin = 0.0 if cfg["fmin"] is None else cfg["fmin"]
+        fmax = cfg["sampling_rate"] / 2 if cfg["fmax"] is None else cfg["fmax"]
+        assert np.array_equal(pl.mel_bank, LO.slaney_mel_filters(cfg["sampling_rate"], cfg["fft_size"], cfg["num_mel_bins"], fmin, fmax).T)
     with pytest.raises(ValueError):
         B200LibrosaFbank(B200LibrosaFbankConfig(window="kaiser"))
     with pytest.raises(AssertionError):
