@@ -202,7 +202,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
       // ---- 2. gather in prime-factor order, DC removal, energy, pre-emphasis, window (layers.py:155-170)
       float2 v[25];
       float e = 0.f;
-      {
+      if (p.preemph != 0.f) {
         int m = 25 * l;  // (25 l + 8 b) mod 200
 #pragma unroll
         for (int bb = 0; bb < 25; ++bb) {
@@ -213,6 +213,20 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
           const float dp = xp - mu;
           if (p.raw_energy) e = fmaf(d.x, d.x, fmaf(d.y, d.y, e));
           const float2 y = __fmul2_rn(__ffma2_rn(make_float2(dp, d.x), make_float2(-p.preemph, -p.preemph), d), w);
+          if (!p.raw_energy) e = fmaf(y.x, y.x, fmaf(y.y, y.y, e));
+          v[bb] = y;
+          m += 8;
+          m = m >= 200 ? m - 200 : m;
+        }
+      } else {  // no pre-emphasis (whisper-fbank, librosa-fbank, preemph_coeff = 0): no neighbour tap to fetch
+        int m = 25 * l;
+#pragma unroll
+        for (int bb = 0; bb < 25; ++bb) {
+          const float2 x = *reinterpret_cast<const float2 *>(S + 2 * m);
+          const float2 w = s_win[bb * 8 + l];
+          const float2 d = f2add(x, make_float2(-mu, -mu));
+          if (p.raw_energy) e = fmaf(d.x, d.x, fmaf(d.y, d.y, e));
+          const float2 y = __fmul2_rn(d, w);
           if (!p.raw_energy) e = fmaf(y.x, y.x, fmaf(y.y, y.y, e));
           v[bb] = y;
           m += 8;

@@ -18,9 +18,13 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
                                               int lane) {
   const int nb = Nc / R;
   const int tstep = Nc / (Ns * R);
+  // Ns is a power of two for as long as only radix-4/2 passes have run (every pass of a power-of-two plan): j % Ns and
+  // j / Ns are then a mask and a shift instead of two ~20-instruction integer divisions per butterfly
+  const bool pow2 = (Ns & (Ns - 1)) == 0;
+  const int sh = 31 - __clz(Ns), msk = Ns - 1;
   if (R == 4) {
     for (int j = lane; j < nb; j += 32) {
-      const int k = j % Ns;
+      const int k = pow2 ? (j & msk) : j % Ns;
       float2 v0 = src[j], v1 = src[j + nb], v2 = src[j + 2 * nb], v3 = src[j + 3 * nb];
       if (k != 0) {
         const int ti = k * tstep;
@@ -32,7 +36,7 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
       const float2 b = make_float2(v0.x - v2.x, v0.y - v2.y);
       const float2 c = make_float2(v1.x + v3.x, v1.y + v3.y);
       const float2 d = make_float2(v1.y - v3.y, v3.x - v1.x);  // -i * (v1 - v3)
-      const int o = (j / Ns) * Ns * 4 + k;
+      const int o = (pow2 ? (j >> sh) : j / Ns) * Ns * 4 + k;
       dst[o] = make_float2(a.x + c.x, a.y + c.y);
       dst[o + Ns] = make_float2(b.x + d.x, b.y + d.y);
       dst[o + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
@@ -40,10 +44,10 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
     }
   } else if (R == 2) {
     for (int j = lane; j < nb; j += 32) {
-      const int k = j % Ns;
+      const int k = pow2 ? (j & msk) : j % Ns;
       float2 v0 = src[j], v1 = src[j + nb];
       if (k != 0) v1 = cmul(v1, __ldg(tw + k * tstep));
-      const int o = (j / Ns) * Ns * 2 + k;
+      const int o = (pow2 ? (j >> sh) : j / Ns) * Ns * 2 + k;
       dst[o] = make_float2(v0.x + v1.x, v0.y + v1.y);
       dst[o + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
     }
