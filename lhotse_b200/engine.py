@@ -289,12 +289,13 @@ class Engine:
         else:
             Ts = (ns + p.S // 2) // p.S
         prefix = np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
-        out = torch.empty((int(prefix[-1]), self.feature_dim), dtype=torch.float32, pin_memory=True).numpy()
+        pin = torch.cuda.is_available()
+        out = torch.empty((int(prefix[-1]), self.feature_dim), dtype=torch.float32, pin_memory=pin).numpy()
         esz = 2 if np.dtype(dtype) == np.int16 else 4
         groups = _groups(lens, sub_bytes, esz, ramp=True)
         tdt = torch.int16 if esz == 2 else torch.float32
         cap = max(_aligned_offsets(lens[b0:b1], 4)[1] for b0, b1 in groups)
-        bufs = [torch.empty(cap, dtype=tdt, pin_memory=True) for _ in range(min(2, len(groups)))]
+        bufs = [torch.empty(cap, dtype=tdt, pin_memory=pin) for _ in range(min(2, len(groups)))]
         stager = (lambda j: stage_host(arrays[groups[j][0]: groups[j][1]], dtype=dtype, out=bufs[j % 2]))
         cur, nxt = stager(0), None
         side = ThreadPoolExecutor(max_workers=1) if len(groups) > 1 else None  # drives the staging of j + 1 (fans out to the pool)
