@@ -33,7 +33,7 @@ import numpy as np
 import torch
 
 from .base import FeatureExtractor, register_extractor
-from .engine import OUT_PACKED, OUT_PADDED, Engine, pack_device, stage_host
+from .engine import OUT_PADDED, Engine, pack_device, stage_host
 from .plan import EPSILON, LOG_EPSILON, FeaturePlan, build_plan
 
 Seconds = float

@@ -32,7 +32,7 @@ from __future__ import annotations
 
 from dataclasses import asdict, dataclass, field
 from functools import partial
-from typing import Any, Dict, List, Optional, Sequence, Union
+from typing import Any, Dict, Optional, Union
 
 import numpy as np
 import torch
