@@ -34,3 +34,12 @@ from .families import (  # noqa: F401
 from .engine import Engine, B200FeatError, load_library  # noqa: F401
 
 __version__ = "0.1.0"
+
+# LHOTSE_B200_INSTALL_AS_DEFAULT=1: re-point lhotse's own registry names ("kaldi-fbank", "fbank", "whisper-fbank", ...) at the
+# B200 classes on import, so that YAML-driven entry points (FeatureExtractor.from_yaml, the `lhotse feat extract` CLI) pick
+# them up with nothing but `import lhotse_b200` (e.g. from sitecustomize / a recipe's __init__)
+import os as _os
+
+if _os.environ.get("LHOTSE_B200_INSTALL_AS_DEFAULT", "0") not in ("", "0"):
+    install_as_default()
+
