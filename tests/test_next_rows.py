@@ -150,6 +150,9 @@ def test_archive_backend_and_fused_store(env, tmp_path):
             assert np.array_equal(g.load_features(), w_.load_features())
             part = g.features.load(start=g.start + 0.2, duration=0.3)
             assert np.array_equal(part, w_.features.load(start=w_.start + 0.2, duration=0.3))
+    # no manifest path: everything stays in memory (set.py:2290-2294), eager CutSet back
+    mem = compute_and_store_features_fused(cuts, ext, root / "fused_mem", batch_duration=100.0, num_workers=0, overwrite=True)
+    assert [c_.id for c_ in mem] == [c_.id for c_ in want] and all(np.array_equal(a_.load_features(), b_.load_features()) for a_, b_ in zip(mem, want))
     # resumable like the reference: a second call with the same manifest does not recompute anything
     calls = []
     orig = ext.extract_batch_packed
