@@ -139,11 +139,14 @@ def barrier():
 
 
 def compute_and_store_features_sharded(cuts, extractor, storage_path, rank: Optional[int] = None,
-                                       world: Optional[int] = None, manifest_name: str = "cuts", **kwargs):
+                                       world: Optional[int] = None, manifest_name: str = "cuts", fused: bool = False,
+                                       **kwargs):
     """§8e partitioning through lhotse's own batch caller: rank r of W extracts cuts r::W with
     ``CutSet.compute_and_store_features_batch`` (lhotse/cut/set.py:2197) into ``storage_path/feats-{r}``
     and writes ``storage_path/{manifest_name}-{r}.jsonl.gz`` — the layout the reference's ``num_jobs`` split
     produces (set.py:2158-2195), so lhotse's resume logic (``overwrite=False``) and ``combine`` apply per shard.
+    With ``fused=True`` the shard goes through ``lhotse_b200.storage.compute_and_store_features_fused`` instead (one
+    packed extraction, one D2H copy, one append to ``storage_path/feats-{r}.b200feat`` per batch; same manifests).
     Returns this rank's CutSet with features attached.  Needs lhotse."""
     from pathlib import Path
 
@@ -156,6 +159,12 @@ def compute_and_store_features_sharded(cuts, extractor, storage_path, rank: Opti
     storage_path = Path(storage_path)
     storage_path.mkdir(parents=True, exist_ok=True)
     mine = CutSet.from_cuts(shard_iter(cuts, rank, world))
+    if fused:
+        from .storage import compute_and_store_features_fused
+
+        allowed = {k: v for k, v in kwargs.items() if k in ("batch_duration", "num_workers", "overwrite", "pcm16_fast_path")}
+        return compute_and_store_features_fused(mine, extractor, storage_path / f"feats-{rank}",
+                                                manifest_path=storage_path / f"{manifest_name}-{rank}.jsonl.gz", **allowed)
     return mine.compute_and_store_features_batch(
         extractor=extractor,
         storage_path=storage_path / f"feats-{rank}",

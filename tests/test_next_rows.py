@@ -101,6 +101,15 @@ def test_rank_sharded_extraction_roundtrip(env):
         assert [c.id for c in mine] == [c.id for c in cuts][r::2]
     allc = lbd.combine_shards(out, world=2)
     assert [c.id for c in allc] == [c.id for c in cuts]
+    # the same sharding over the fused store (one archive per rank)
+    out2 = root / "sharded_fused"
+    for r in range(2):
+        lbd.compute_and_store_features_sharded(cuts, ext, out2, rank=r, world=2, num_workers=0, batch_duration=4.0,
+                                               fused=True, overwrite=True)
+    fused = lbd.combine_shards(out2, world=2)
+    assert [c.id for c in fused] == [c.id for c in cuts]
+    for a, b in zip(fused, allc):
+        assert a.features.storage_type == "b200_archive" and np.array_equal(a.load_features(), b.load_features())
     for c in allc:
         assert c.has_features and c.features.type == "b200-fbank"
         f = c.load_features()
