@@ -152,6 +152,10 @@ const char *b200feat_last_error(const b200feat_handle *h);
 /* T for a cut of n samples (layers.py:747-753); B200FEAT_ESHORT if it cannot be framed
  * (n too short for a single reflection — the reference raises on those). */
 int64_t b200feat_num_frames(const b200feat_handle *h, int64_t num_samples);
+/* The same integer contract without a handle (and without a GPU): rows a cut of `num_samples` gets under `desc`, or
+ * B200FEAT_ESHORT / B200FEAT_EINVAL.  Pure host arithmetic — lets build-time checks and CPU-only callers (manifest
+ * validation: lhotse/qa.py:267-311 compares num_frames with compute_num_frames) agree with the kernels bit for bit. */
+int64_t b200feat_desc_num_frames(const b200feat_plan_desc *desc, int64_t num_samples);
 /* F: M (+1 with use_energy) for fbank, M for whisper-fbank / log10-fbank, C for mfcc, N/2+1 for the spectrogram kinds. */
 int32_t b200feat_feature_dim(const b200feat_handle *h);
 /* B200FEAT_KERNEL_GENERIC or B200FEAT_KERNEL_FAST — what AUTO resolved to. */

@@ -334,6 +334,14 @@ int64_t b200feat_num_frames(const b200feat_handle *h, int64_t n) {
   return T;
 }
 
+int64_t b200feat_desc_num_frames(const b200feat_plan_desc *desc, int64_t n) {
+  if (!desc || desc->struct_size != (int32_t)sizeof(b200feat_plan_desc) || desc->frame_length <= 0 || desc->frame_shift <= 0 ||
+      desc->fft_length < desc->frame_length || n < 0)
+    return B200FEAT_EINVAL;
+  const int64_t T = frames_for(*desc, n);
+  return framable(*desc, n, T) ? T : (int64_t)B200FEAT_ESHORT;
+}
+
 int32_t b200feat_feature_dim(const b200feat_handle *h) { return h ? h->plan.F : B200FEAT_EINVAL; }
 int32_t b200feat_kernel_kind(const b200feat_handle *h) { return h ? h->kernel : B200FEAT_EINVAL; }
 int64_t b200feat_meta_words(int32_t batch) { return 4 * (int64_t)batch + 2; }

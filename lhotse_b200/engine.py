@@ -61,7 +61,7 @@ EXPORTS = [
     "b200feat_version", "b200feat_global_error", "b200feat_create", "b200feat_destroy",
     "b200feat_last_error", "b200feat_num_frames", "b200feat_feature_dim", "b200feat_kernel_kind",
     "b200feat_meta_words", "b200feat_plan_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
-    "b200feat_extract_host_at",
+    "b200feat_extract_host_at", "b200feat_desc_num_frames",
     "b200feat_get_table", "b200feat_get_stats",
 ]
 
@@ -112,6 +112,8 @@ def load_library():
         lib.b200feat_extract_host.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.c_float]
         lib.b200feat_extract_host_at.restype = C.c_int
         lib.b200feat_extract_host_at.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, C.c_float]
+        lib.b200feat_desc_num_frames.restype = i64
+        lib.b200feat_desc_num_frames.argtypes = [C.POINTER(PlanDesc), i64]
         lib.b200feat_get_table.restype = i64
         lib.b200feat_get_table.argtypes = [vp, i32, vp, i64]
         lib.b200feat_get_stats.restype = C.c_int
@@ -120,6 +122,30 @@ def load_library():
             raise ImportError("libb200feat.so ABI version mismatch")
         _LIB = lib
         return lib
+
+
+def plan_desc(plan: FeaturePlan, kernel: str = "auto") -> PlanDesc:
+    """FeaturePlan -> b200feat_plan_desc (include/b200feat.h)."""
+    d = PlanDesc()
+    d.struct_size = C.sizeof(PlanDesc)
+    d.feature = FEATURE_KINDS[plan.feature]
+    d.frame_length, d.frame_shift, d.fft_length = plan.L, plan.S, plan.N
+    d.num_filters, d.num_ceps = plan.num_filters, plan.num_ceps
+    d.snip_edges, d.remove_dc_offset = int(plan.snip_edges), int(plan.remove_dc_offset)
+    d.use_energy, d.raw_energy, d.use_fft_mag = int(plan.use_energy), int(plan.raw_energy), int(plan.use_fft_mag)
+    d.energy_style = plan.energy_style
+    d.use_lifter = int(plan.lifter is not None)
+    d.kernel = KERNELS[kernel]
+    d.pad_mode = int(getattr(plan, "pad_mode", 0))
+    d.preemph_coeff, d.energy_floor = plan.preemph_coeff, plan.energy_floor
+    d.mel_floor, d.log_spec_eps = plan.mel_floor, plan.log_spec_eps
+    return d
+
+
+def desc_num_frames(plan: FeaturePlan, num_samples: int) -> int:
+    """Rows the kernels produce for a cut of `num_samples` under `plan` — the C library's own integer contract, callable
+    without a GPU (negative: B200FEAT_ESHORT -5 when the cut cannot be framed)."""
+    return int(load_library().b200feat_desc_num_frames(C.byref(plan_desc(plan)), int(num_samples)))
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -138,19 +164,7 @@ class Engine:
         self.device_index = dev.index if dev.index is not None else (
             torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.device = torch.device("cuda", self.device_index)
-        d = PlanDesc()
-        d.struct_size = C.sizeof(PlanDesc)
-        d.feature = FEATURE_KINDS[plan.feature]
-        d.frame_length, d.frame_shift, d.fft_length = plan.L, plan.S, plan.N
-        d.num_filters, d.num_ceps = plan.num_filters, plan.num_ceps
-        d.snip_edges, d.remove_dc_offset = int(plan.snip_edges), int(plan.remove_dc_offset)
-        d.use_energy, d.raw_energy, d.use_fft_mag = int(plan.use_energy), int(plan.raw_energy), int(plan.use_fft_mag)
-        d.energy_style = plan.energy_style
-        d.use_lifter = int(plan.lifter is not None)
-        d.kernel = KERNELS[kernel]
-        d.pad_mode = int(getattr(plan, "pad_mode", 0))
-        d.preemph_coeff, d.energy_floor = plan.preemph_coeff, plan.energy_floor
-        d.mel_floor, d.log_spec_eps = plan.mel_floor, plan.log_spec_eps
+        d = plan_desc(plan, kernel)
         tabs = [None if t is None else np.ascontiguousarray(t, dtype=np.float32)
                 for t in (plan.window, plan.mel_bank, plan.dct, plan.lifter)]
         h = C.c_void_p()
