@@ -17,6 +17,11 @@
  *   spectrogram kinds .......... layers.py:392-402, :461-473
  *   mel + log .................. layers.py:565-578
  *   dct + lifter ............... layers.py:708-724
+ * and, for the centre-padded STFT front ends (oracle_extract_center below):
+ *   WhisperFbank ............... lhotse/features/whisper_fbank.py:16-84 (torch.stft(center=True), |X|^2, mel, log10,
+ *                                clamp to the utterance maximum - 8, (x + 4) / 4, zero row up to compute_num_frames)
+ *   LibrosaFbank ............... lhotse/features/librosa_fbank.py:64-135 (librosa.stft(pad_mode="reflect"), |X|, mel,
+ *                                log10(max(eps, .)), pad_or_truncate_features)
  */
 #include <math.h>
 #include <stdint.h>
@@ -159,3 +164,57 @@ int oracle_extract(const oracle_plan *p, const float *x, int64_t n, const float 
   free(f); free(spec); free(mel); free(re); free(im); free(cs); free(sn);
   return 0;
 }
+
+/*
+ * Centre-padded log10-mel front ends.  kind 4 = whisper-fbank, kind 5 = librosa-fbank; N = n_fft (frame = N samples under
+ * `window`, which already holds a shorter window centred and zero-padded), S = hop, reflect padding of N/2 samples per side
+ * WITHOUT repeating the edge sample.  `use_mag`: |X| (librosa) or |X|^2 (whisper).  Output rows = (n + S/2) / S.
+ * Returns 0, or -1 when n <= N/2 (reflect padding impossible: torch / numpy raise there).
+ */
+int oracle_extract_center(int32_t kind, int32_t N, int32_t S, int32_t M, int32_t use_mag, float floor_, const float *x,
+                          int64_t n, const float *window /* N */, const float *mel_bank /* K x M */, float *out) {
+  const int K = N / 2 + 1;
+  if (n <= N / 2) return -1;
+  const int64_t rows = (n + S / 2) / S;
+  const int64_t Tstft = kind == 4 ? n / S : 1 + n / S; /* whisper drops the stft's last frame (whisper_fbank.py:63) */
+  const int64_t Tv = Tstft < rows ? Tstft : rows;
+  float *f = (float *)malloc(sizeof(float) * (size_t)N);
+  double *re = (double *)malloc(sizeof(double) * (size_t)K), *im = (double *)malloc(sizeof(double) * (size_t)K);
+  double *cs = (double *)malloc(sizeof(double) * (size_t)N), *sn = (double *)malloc(sizeof(double) * (size_t)N);
+  for (int j = 0; j < N; ++j) {
+    cs[j] = cos(2.0 * M_PI * (double)j / (double)N);
+    sn[j] = sin(2.0 * M_PI * (double)j / (double)N);
+  }
+  float vmax = -INFINITY;
+  for (int64_t t = 0; t < Tv; ++t) {
+    for (int j = 0; j < N; ++j) {
+      int64_t i = t * S + j - N / 2;
+      if (i < 0) i = -i;
+      if (i >= n) i = 2 * n - 2 - i;
+      f[j] = x[i] * window[j];
+    }
+    rdft(f, N, re, im, cs, sn);
+    for (int m = 0; m < M; ++m) {
+      float acc = 0.0f;
+      for (int k = 0; k < K; ++k) {
+        const float w = mel_bank[(size_t)k * M + m];
+        if (w != 0.0f) {
+          const double pw = re[k] * re[k] + im[k] * im[k];
+          acc += (use_mag ? (float)sqrt(pw) : (float)pw) * w;
+        }
+      }
+      const float v = log10f(acc > floor_ ? acc : floor_);
+      out[t * M + m] = v;
+      if (v > vmax) vmax = v;
+    }
+  }
+  if (kind == 4)
+    for (int64_t i = 0; i < Tv * M; ++i) {
+      const float v = out[i] > vmax - 8.0f ? out[i] : vmax - 8.0f;
+      out[i] = (v + 4.0f) / 4.0f;
+    }
+  for (int64_t i = Tv * M; i < rows * M; ++i) out[i] = kind == 4 ? 0.0f : (float)log(1e-10); /* :73-80 / librosa_fbank.py:51-56 */
+  free(f); free(re); free(im); free(cs); free(sn);
+  return 0;
+}
+

@@ -66,3 +66,55 @@ def test_c_oracle_rejects_short_inputs(lib):
     x = np.zeros(100, dtype=np.float32)
     out = np.empty((1, 80), dtype=np.float32)
     assert lib.oracle_extract(C.byref(p), _ptr(x), C.c_int64(100), _ptr(plan.window), _ptr(plan.mel_bank), None, None, _ptr(out)) == -1
+
+
+def _center_goldens():
+    import json
+
+    out = []
+    here = os.path.dirname(os.path.abspath(__file__))
+    for kind, fname in ((4, "golden_whisper_v1.npz"), (5, "golden_librosa_v1.npz")):
+        g = np.load(os.path.join(here, "golden", fname))
+        for i, c in enumerate(json.loads(bytes(g["manifest"]).decode())):
+            if c["n"] <= 32000 and (kind == 4 or c["cfg"]["fft_size"] <= 1024):  # the O(N^2) DFT keeps these in seconds
+                out.append((kind, i, c, g[f"x{i}"], g[f"y{i}"]))
+    return out
+
+
+CENTER = _center_goldens()
+
+
+@pytest.mark.parametrize("kind,i,c,x,y", CENTER, ids=[f"{'whisper' if k == 4 else 'librosa'}-{i}-{c['n']}" for k, i, c, _, _ in CENTER])
+def test_c_oracle_center_front_ends_match_golden(lib, kind, i, c, x, y):
+    """Third, plain-C restatement of the Whisper / Librosa front ends (oracle_extract_center) against the vectors produced by
+    the reference classes; tables come from the product's plan builder (pinned separately in test_whisper / test_librosa)."""
+    from lhotse_b200 import B200LibrosaFbankConfig, B200WhisperFbankConfig
+
+    if kind == 4:
+        plan = build_plan("whisper-fbank", B200WhisperFbankConfig(num_filters=c["num_filters"]))
+    else:
+        plan = build_plan("librosa-fbank", B200LibrosaFbankConfig(**c["cfg"]))
+    out = np.empty(y.shape, dtype=np.float32)
+    lib.oracle_extract_center.restype = C.c_int
+    rc = lib.oracle_extract_center(C.c_int32(kind), C.c_int32(plan.N), C.c_int32(plan.S), C.c_int32(plan.num_filters),
+                                   C.c_int32(int(plan.use_fft_mag)), C.c_float(plan.mel_floor), _ptr(np.ascontiguousarray(x)),
+                                   C.c_int64(len(x)), _ptr(plan.window), _ptr(plan.mel_bank), _ptr(out))
+    assert rc == 0
+    if kind == 4:  # the reference's fp32 STFT vs this double-precision DFT: last-bits differences only
+        np.testing.assert_allclose(out, y, rtol=0, atol=6e-5)
+    else:          # float32 window table / float32 product here, float64 in librosa: same amplitude-floor gate as the GPU test
+        from test_librosa import librosa_gate
+
+        ok, msg = librosa_gate(out, y.astype(np.float64), c["cfg"])
+        assert ok, msg
+
+
+def test_c_oracle_center_rejects_short_inputs(lib):
+    from lhotse_b200 import B200WhisperFbankConfig
+
+    plan = build_plan("whisper-fbank", B200WhisperFbankConfig())
+    out = np.empty((2, 80), dtype=np.float32)
+    lib.oracle_extract_center.restype = C.c_int
+    assert lib.oracle_extract_center(C.c_int32(4), C.c_int32(400), C.c_int32(160), C.c_int32(80), C.c_int32(0), C.c_float(1e-10),
+                                     _ptr(np.zeros(200, dtype=np.float32)), C.c_int64(200), _ptr(plan.window),
+                                     _ptr(plan.mel_bank), _ptr(out)) == -1
