@@ -75,7 +75,8 @@ class B200ArchiveWriter(FeaturesWriter):
         if value.ndim != 2:
             raise ValueError(f"b200_archive stores (frames, features) matrices, got shape {value.shape}")
         off = self._pos
-        self._f.write(memoryview(value).cast("B"))
+        if value.size:  # (memoryview cannot cast an empty matrix)
+            self._f.write(memoryview(value).cast("B"))
         self._pos += value.nbytes
         return f"{off},{value.shape[0]},{value.shape[1]}"
 
@@ -85,7 +86,8 @@ class B200ArchiveWriter(FeaturesWriter):
         packed = np.ascontiguousarray(packed, dtype="<f4")
         assert packed.ndim == 2 and len(row_prefix) == len(keys) + 1 and int(row_prefix[-1]) == packed.shape[0]
         base, F = self._pos, packed.shape[1]
-        self._f.write(memoryview(packed).cast("B"))
+        if packed.size:
+            self._f.write(memoryview(packed).cast("B"))
         self._pos += packed.nbytes
         return [f"{base + int(row_prefix[i]) * F * 4},{int(row_prefix[i + 1]) - int(row_prefix[i])},{F}" for i in range(len(keys))]
 
