@@ -141,6 +141,18 @@ class B200ArchiveReader(FeaturesReader):
             pass
 
 
+def register_with_lhotse() -> bool:
+    """(Re-)registers the archive backend in lhotse's reader / writer registries (io.py:283-313).  Done at import when lhotse
+    is importable; callable later for processes where lhotse only became importable after this module was loaded."""
+    try:
+        from lhotse.features.io import READER_BACKENDS, WRITER_BACKENDS
+    except Exception:
+        return False
+    WRITER_BACKENDS[B200ArchiveWriter.name] = B200ArchiveWriter
+    READER_BACKENDS[B200ArchiveReader.name] = B200ArchiveReader
+    return True
+
+
 def compute_and_store_features_fused(
     cuts,
     extractor,
@@ -166,6 +178,7 @@ def compute_and_store_features_fused(
 
     from .pcm_staging import PcmStagingRing, pcm16_request_for_cut
 
+    register_with_lhotse()
     frame_shift = extractor.frame_shift
     cuts_writer = CutSet.open_writer(manifest_path, overwrite=overwrite)
     sampler = SimpleCutSampler(cuts, max_duration=batch_duration)

@@ -21,6 +21,9 @@ def env(tmp_path_factory):
 
     importlib.reload(lb_base)
     importlib.reload(lb_ex)
+    import lhotse_b200.storage as lb_st
+
+    importlib.reload(lb_st)  # subclass lhotse's FeaturesWriter / FeaturesReader now that they are importable
     from lhotse import CutSet, MonoCut, Recording, SupervisionSegment
     from lhotse.audio import AudioSource
     from lhotse.audio.backend import AudioBackend, LibsndfileCompatibleAudioInfo, set_current_audio_backend
