@@ -39,7 +39,7 @@ import torch
 
 from .base import FeatureExtractor, register_extractor
 from .extractors import B200Fbank, B200LogSpectrogram, B200LogSpectrogramConfig, from_reference_config
-from .plan import EPSILON
+from .plan import EPSILON, LOG_EPSILON
 
 Seconds = float
 ArrayLike = Union[np.ndarray, torch.Tensor]
@@ -252,6 +252,19 @@ class _FamilyExtractor(FeatureExtractor):
         for inner in self._inner_by_sr.values():
             inner.to(device)
         self._inner_by_sr = {}
+
+    # the batch entry points of the fused callers (input_strategies.FusedOnTheFlyFeatures, storage.compute_and_store_features_fused)
+    def extract_batch_padded(self, samples, sampling_rate: int, padding_value: float = LOG_EPSILON):
+        return self._inner(sampling_rate).extract_batch_padded(samples, sampling_rate, padding_value=padding_value)
+
+    def extract_batch_packed(self, samples, sampling_rate: int):
+        return self._inner(sampling_rate).extract_batch_packed(samples, sampling_rate)
+
+    def extract_staged_padded(self, staged, lens, offsets, sampling_rate: int, padding_value: float = LOG_EPSILON):
+        return self._inner(sampling_rate).extract_staged_padded(staged, lens, offsets, sampling_rate, padding_value=padding_value)
+
+    def extract_staged_packed(self, staged, lens, offsets, sampling_rate: int):
+        return self._inner(sampling_rate).extract_staged_packed(staged, lens, offsets, sampling_rate)
 
     # log-mel energies: same statics as the reference classes (fbank.py:57-76, kaldifeat.py:196-215)
     mix = staticmethod(B200Fbank.mix)

@@ -27,6 +27,7 @@ class FusedOnTheFlyFeatures:
         extractor,
         wave_transforms: Optional[List[Callable[[torch.Tensor], torch.Tensor]]] = None,
         num_workers: int = 0,
+        use_batch_extract: bool = True,
         fault_tolerant: bool = False,
         return_audio: bool = False,
         executor_type: Type = ThreadPoolExecutor,
@@ -38,6 +39,10 @@ class FusedOnTheFlyFeatures:
         self.extractor = extractor
         self.wave_transforms = list(wave_transforms or [])
         self.num_workers = num_workers
+        # same position and meaning as the reference's argument (input_strategies.py:374, :391-394): True = one sampling rate
+        # per batch (asserted); False = mixed sampling rates allowed — here one launch per sampling rate instead of one
+        # `extract` call per cut
+        self.use_batch_extract = use_batch_extract
         self.fault_tolerant = fault_tolerant
         self.return_audio = return_audio
         self.features_on_device = features_on_device
@@ -62,6 +67,8 @@ class FusedOnTheFlyFeatures:
             return None
         from .pcm_staging import PcmStagingRing, pcm16_request_for_cut
 
+        if len({c.sampling_rate for c in cuts}) != 1:
+            return None  # mixed sampling rates: grouped by the float route
         reqs = []
         for c in cuts:
             r = pcm16_request_for_cut(c)
@@ -99,8 +106,11 @@ class FusedOnTheFlyFeatures:
             for idx in range(len(audios)):
                 audios[idx] = tfnm(audios[idx])
         sr = cuts[0].sampling_rate
-        assert all(c.sampling_rate == sr for c in cuts), "all cuts of a batch must share one sampling rate"
-        feats, feat_lens = self.extractor.extract_batch_padded(audios, sr, padding_value=LOG_EPSILON)
+        if all(c.sampling_rate == sr for c in cuts):
+            feats, feat_lens = self.extractor.extract_batch_padded(audios, sr, padding_value=LOG_EPSILON)
+        else:
+            assert not self.use_batch_extract, "all cuts of a batch must share one sampling rate (or pass use_batch_extract=False)"
+            feats, feat_lens = self._extract_mixed_rates(audios, [c.sampling_rate for c in cuts])
         if not self.features_on_device:
             feats = feats.cpu()
         out = (feats, feat_lens)
@@ -111,6 +121,25 @@ class FusedOnTheFlyFeatures:
         if self.fault_tolerant:
             out = out + (cuts,)
         return out
+
+    def _extract_mixed_rates(self, audios, rates):
+        """One padded extraction per sampling rate (needs an extractor that accepts them, e.g. the torchaudio family),
+        scattered back into one (B, T_max, F) tensor in the batch's order."""
+        groups = {}
+        for i, r in enumerate(rates):
+            groups.setdefault(int(r), []).append(i)
+        parts = {r: self.extractor.extract_batch_padded([audios[i] for i in idx], r, padding_value=LOG_EPSILON)
+                 for r, idx in groups.items()}
+        tmax = max(int(p[0].shape[1]) for p in parts.values())
+        first = next(iter(parts.values()))[0]
+        feats = torch.full((len(audios), tmax, first.shape[2]), LOG_EPSILON, dtype=first.dtype, device=first.device)
+        feat_lens = torch.zeros(len(audios), dtype=torch.int64)
+        for r, idx in groups.items():
+            f, l = parts[r]
+            sel = torch.tensor(idx, dtype=torch.int64)
+            feats[sel.to(feats.device), : f.shape[1]] = f
+            feat_lens[sel] = l
+        return feats, feat_lens
 
     # lhotse's BatchIO protocol (input_strategies.py:52-110): used by K2SpeechRecognitionDataset for supervisions
     def supervision_intervals(self, cuts):

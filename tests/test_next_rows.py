@@ -172,3 +172,45 @@ def test_archive_backend_and_fused_store(env, tmp_path):
     again = compute_and_store_features_fused(cuts, ext, root / "fused_False", manifest_path=root / "fused_False.jsonl.gz",
                                              batch_duration=4.0, num_workers=0, pcm16_fast_path=False)
     assert len(list(again)) == len(cuts) and not calls
+
+
+def test_fused_on_the_fly_mixed_sampling_rates_and_family_adapters(env, tmp_path):
+    """`use_batch_extract=False` (reference: sequential `extract` so that sampling rates may differ, input_strategies.py:447-459):
+    here one padded extraction per sampling rate, through an extractor that takes the rate per call (torchaudio family)."""
+    import importlib
+
+    from helpers import attach_oracle_engine
+    from lhotse import CutSet, MonoCut, Recording
+    from lhotse.audio import AudioSource
+    from lhotse.dataset.input_strategies import OnTheFlyFeatures
+
+    import lhotse_b200.families as fam
+    from lhotse_b200.input_strategies import FusedOnTheFlyFeatures
+
+    importlib.reload(fam)
+    rs = np.random.RandomState(5)
+    cuts = []
+    for i, (sr, dur) in enumerate(((16000, 1.0), (8000, 1.5), (16000, 0.7), (8000, 0.5))):
+        n = int(sr * dur)
+        path = tmp_path / f"m{i}.wav"
+        with wave.open(str(path), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr)
+            w.writeframes(np.clip(rs.randn(n) * 3000, -32768, 32767).astype("<i2").tobytes())
+        rec = Recording(id=f"m{i}", sources=[AudioSource(type="file", channels=[0], source=str(path))],
+                        sampling_rate=sr, num_samples=n, duration=n / sr)
+        cuts.append(MonoCut(id=f"m{i}", start=0.0, duration=n / sr, channel=0, recording=rec))
+    cs = CutSet.from_cuts(cuts)
+    ext = fam.B200TorchaudioFbank()
+    for sr in (8000, 16000):
+        attach_oracle_engine(ext._inner(sr))
+    want, want_lens = OnTheFlyFeatures(ext, use_batch_extract=False)(cs)          # the reference strategy, cut by cut
+    fused = FusedOnTheFlyFeatures(ext, None, 0, False)                              # same positional arguments
+    got, got_lens = fused(cs)
+    assert fused.use_batch_extract is False and torch.equal(got_lens, want_lens) and got_lens.tolist() == [100, 150, 70, 50]
+    assert got.shape == want.shape and torch.equal(got, want)
+    with pytest.raises(AssertionError):
+        FusedOnTheFlyFeatures(ext)(cs)                                              # default: one sampling rate per batch
+    same = CutSet.from_cuts([cuts[0], cuts[2]])
+    a, la = FusedOnTheFlyFeatures(ext)(same)                                        # family adapter on the single-rate route
+    b, lb_ = OnTheFlyFeatures(ext)(same)
+    assert torch.equal(la, lb_) and torch.equal(a, b)
