@@ -161,7 +161,8 @@ def test_dropin_through_reference_callers(tmp_path):
     set_current_audio_backend(WaveBackend())
     rs = np.random.RandomState(0)
     cuts = []
-    for i in range(6):  # BASELINE config 1 in miniature: 1 s synthetic MonoCuts @ 16 kHz
+    NCUTS = 100
+    for i in range(NCUTS):  # BASELINE configs[0]: 100 synthetic 1 s MonoCuts @ 16 kHz through compute_and_store_features
         path = tmp_path / f"c{i}.wav"
         pcm = np.clip(rs.randn(16000) * 0.1 * 32768, -32768, 32767).astype("<i2")
         with wave.open(str(path), "wb") as w:
@@ -181,8 +182,9 @@ def test_dropin_through_reference_callers(tmp_path):
         want = O.extract(cut.load_audio()[0], O.OracleConfig())
         assert np.array_equal(feats, want)
     assert cuts[0].compute_features(ext).shape == (100, 80)
+    assert len(list(out)) == NCUTS
     feats, lens = OnTheFlyFeatures(ext)(cs)
-    assert feats.shape == (6, 100, 80) and lens.tolist() == [100] * 6
+    assert feats.shape == (NCUTS, 100, 80) and lens.tolist() == [100] * NCUTS
     # registry round trip through the reference's own from_dict
     again = RefFE.from_dict(ext.to_dict())
     assert type(again).__name__ == "B200Fbank"
