@@ -85,7 +85,7 @@ extern "C" {
 #define B200FEAT_KERNEL_AUTO 0
 #define B200FEAT_KERNEL_GENERIC 1 /* any L/S/N, mixed-radix Stockham in shared memory */
 #define B200FEAT_KERNEL_FAST 2    /* register-resident rFFT: N = 512 (radix 16x16, one frame per half-warp) or N = 256 (16x8, per quarter-warp) */
-#define B200FEAT_KERNEL_FAST_X2 3 /* same algorithm, two frames per half-warp in packed f32x2 (FFMA2/FADD2); experimental */
+#define B200FEAT_KERNEL_TC 3      /* tensor cores: the N = 512 real DFT as two tcgen05.mma (3xTF32) GEMM stages, 16 frames per tile; fbank / mfcc */
 
 typedef struct b200feat_plan_desc {
   int32_t struct_size;  /* sizeof(b200feat_plan_desc) — ABI guard */

@@ -12,7 +12,7 @@
 #include "common.cuh"
 #include "generic.cuh"
 #include "fast512.cuh"
-#include "fast512x2.cuh"
+#include "tc512.cuh"
 #include "fast256.cuh"
 #include "fast1024.cuh"
 #include "fast400.cuh"
@@ -50,7 +50,7 @@ struct b200feat_handle {
   std::mutex stats_mu;
   HostRing ring;
   Fast512Host fast;
-  FastX2Host fastx2;
+  Tc512Host tc;
   Fast256Host fast256;
   Fast1024Host fast1024;
   Fast400Host fast400;
@@ -248,25 +248,27 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   if (desc->use_lifter) UP(upload(h, h->h_lifter.data(), h->h_lifter.size(), &p.lifter));
 
   // ---- kernel selection
-  // the whisper-fbank epilogue / centre padding exist in the generic and the fast400 kernels only
-  // (fast512x2 has neither centre padding nor the log10 epilogue; it is an explicit, experimental choice anyway)
-  if (desc->kernel == B200FEAT_KERNEL_FAST_X2 && (whisper || log10fb)) {
+  // the whisper-fbank epilogue / centre padding exist in the generic and the fast400 kernels only; the tensor-core kernel
+  // (tc512.cuh) serves the N = 512 fbank / mfcc plans without an energy column
+  const bool tc_ok = !whisper && tc512_supported(p);
+  if (desc->kernel == B200FEAT_KERNEL_TC && !tc_ok) {
     cudaSetDevice(prev); b200feat_destroy(h);
-    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast_x2 supports the Kaldi kinds only");
+    return fail(nullptr, B200FEAT_EUNSUPPORTED, "the tensor-core kernel needs fft_length 512, fbank / mfcc without use_energy, Kaldi framing");
   }
-  const bool fast512_ok = !whisper && fastx2_supported(p) && fast512_supported(p);
-  const bool fast256_ok = !whisper && fast256_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
-  const bool fast1024_ok = !whisper && fast1024_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
-  const bool fast400_ok = fast400_supported(p) && desc->kernel != B200FEAT_KERNEL_FAST_X2;
+  const bool fast512_ok = !whisper && fast512_supported(p);
+  const bool fast256_ok = !whisper && fast256_supported(p);
+  const bool fast1024_ok = !whisper && fast1024_supported(p);
+  const bool fast400_ok = fast400_supported(p);
   const bool fast_ok = fast512_ok || fast256_ok || fast1024_ok || fast400_ok;
-  const bool want_fast = desc->kernel == B200FEAT_KERNEL_FAST || desc->kernel == B200FEAT_KERNEL_FAST_X2;
-  if (want_fast && !fast_ok) {
+  if (desc->kernel == B200FEAT_KERNEL_FAST && !fast_ok) {
     cudaSetDevice(prev); b200feat_destroy(h);
-    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 256, 512, 1024 or frame_length = fft_length = 400 (fast_x2: 512 only)");
+    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 256, 512, 1024 or frame_length = fft_length = 400");
   }
-  if (desc->kernel == B200FEAT_KERNEL_GENERIC || !fast_ok) h->kernel = B200FEAT_KERNEL_GENERIC;
-  else if (desc->kernel == B200FEAT_KERNEL_FAST_X2) h->kernel = B200FEAT_KERNEL_FAST_X2;
-  else h->kernel = B200FEAT_KERNEL_FAST;  // AUTO: the scalar kernel is the faster one today (profiles/README.md)
+  bool auto_tc = false;  // AUTO prefers the tensor-core kernel where it is the faster one (B200FEAT_AUTO_TC=0/1 overrides)
+  if (const char *e = getenv("B200FEAT_AUTO_TC")) auto_tc = atoi(e) != 0;
+  if (desc->kernel == B200FEAT_KERNEL_TC || (desc->kernel == B200FEAT_KERNEL_AUTO && tc_ok && auto_tc)) h->kernel = B200FEAT_KERNEL_TC;
+  else if (desc->kernel == B200FEAT_KERNEL_GENERIC || !fast_ok) h->kernel = B200FEAT_KERNEL_GENERIC;
+  else h->kernel = B200FEAT_KERNEL_FAST;
 
   {  // generic launch shape: as many warps per CTA as fit ~100 KB, CTA <= 8 warps
     const size_t per_warp = generic_smem_per_warp(p.N, p.Nc);
@@ -289,12 +291,21 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
     }
   }
   h->frames_per_tile = 1;
-  if (h->kernel != B200FEAT_KERNEL_GENERIC) {
+  if (h->kernel == B200FEAT_KERNEL_TC) {
+    rc = tc512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->tc);
+    if (rc == B200FEAT_EUNSUPPORTED && desc->kernel == B200FEAT_KERNEL_AUTO) {
+      h->kernel = fast_ok ? B200FEAT_KERNEL_FAST : B200FEAT_KERNEL_GENERIC;
+      h->frames_per_tile = 1;
+      rc = 0;
+    } else if (rc) {
+      cudaSetDevice(prev); b200feat_destroy(h);
+      return fail(nullptr, rc, "tensor-core kernel cannot be prepared for this plan");
+    }
+  }
+  if (h->kernel == B200FEAT_KERNEL_FAST) {
     if (h->plan.N == 256) rc = fast256_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast256);
     else if (h->plan.N == 400) rc = fast400_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast400);
     else if (h->plan.N == 1024) rc = fast1024_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast1024);
-    else if (h->kernel == B200FEAT_KERNEL_FAST_X2)
-      rc = fastx2_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fastx2);
     else rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
     if (rc == B200FEAT_EUNSUPPORTED && desc->kernel == B200FEAT_KERNEL_AUTO) {
       h->kernel = B200FEAT_KERNEL_GENERIC;  // e.g. the plan's tables do not fit the fast kernel's shared memory
@@ -441,9 +452,9 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
     cudaError_t e = cudaMemsetAsync(db.cut_max, 0xff, (size_t)db.B * sizeof(float), stream);  // "empty" (common.cuh)
     if (e != cudaSuccess) return fail(h, B200FEAT_ECUDA, std::string("memset(cut_max): ") + cudaGetErrorString(e));
   }
-  if (h->kernel == B200FEAT_KERNEL_FAST_X2) {
-    int rc = fastx2_launch(h->plan, h->fastx2, db, dt, h->sm_count, stream);
-    if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512x2 launch: ") + cudaGetErrorString((cudaError_t)rc));
+  if (h->kernel == B200FEAT_KERNEL_TC) {
+    int rc = tc512_launch(h->plan, h->tc, db, dt, h->sm_count, stream);
+    if (rc) return fail(h, B200FEAT_ECUDA, std::string("tc512 launch: ") + cudaGetErrorString((cudaError_t)rc));
   } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 256) {
     int rc = fast256_launch(h->plan, h->fast256, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast256 launch: ") + cudaGetErrorString((cudaError_t)rc));

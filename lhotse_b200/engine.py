@@ -25,8 +25,8 @@ _LIB_LOCK = threading.Lock()
 
 OUT_PACKED, OUT_PADDED = 0, 1
 DT_F32, DT_I16 = 0, 1
-KERNELS = {"auto": 0, "generic": 1, "fast": 2, "fast_x2": 3}
-KERNEL_NAMES = {1: "generic", 2: "fast", 3: "fast_x2"}
+KERNELS = {"auto": 0, "generic": 1, "fast": 2, "tc": 3}
+KERNEL_NAMES = {1: "generic", 2: "fast", 3: "tc"}
 
 
 class B200FeatError(RuntimeError):
@@ -228,6 +228,10 @@ class Engine:
         default: back to back with 4-element alignment — see `pack_device`).
         Returns (features, row_prefix): packed (sum T, F) or padded (B, Tmax, F)."""
         assert samples.is_cuda and samples.dim() == 1 and samples.is_contiguous()
+        if samples.data_ptr() % 16:
+            # a view with a storage offset (`wave[1:]` is contiguous, so .contiguous() is a no-op): the kernels pick their
+            # 64/128-bit load path from the element offset relative to this pointer and need the pointer itself aligned
+            samples = samples.clone()
         dt = {torch.float32: DT_F32, torch.int16: DT_I16}[samples.dtype]
         B = len(num_samples)
         if meta_dev is None or totals is None:

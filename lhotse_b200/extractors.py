@@ -86,8 +86,9 @@ class B200FbankConfig(_ConfigMixin):
     norm_filters: bool = False
     torchaudio_compatible_mel_scale: bool = True
     device: str = "cuda"
-    kernel: str = "auto"  # auto | fast | fast_x2 | generic
+    kernel: str = "auto"  # auto | fast | tc | generic
     compat: str = "lhotse"  # "torchaudio": Kaldi log-energy convention + 2*pi/(L-1) blackman (TorchaudioFbank / KaldifeatFbank)
+    blackman_coeff: float = 0.42  # window_type="blackman" only (kaldifeat frame_opts.blackman_coeff, kaldifeat.py:24)
 
 
 @dataclass
@@ -118,6 +119,7 @@ class B200MfccConfig(_ConfigMixin):
     device: str = "cuda"
     kernel: str = "auto"
     compat: str = "lhotse"  # "torchaudio": Kaldi log-energy convention, C0 <- energy (TorchaudioMfcc / KaldifeatMfcc)
+    blackman_coeff: float = 0.42  # window_type="blackman" only
 
 
 @dataclass
@@ -140,6 +142,7 @@ class B200SpectrogramConfig(_ConfigMixin):
     device: str = "cuda"
     kernel: str = "auto"
     compat: str = "lhotse"  # "torchaudio" (log-spectrogram only): log(max(P, eps32)), Kaldi log-energy in bin 0 (TorchaudioSpectrogram)
+    blackman_coeff: float = 0.42  # window_type="blackman" only
 
 
 @dataclass
@@ -311,17 +314,23 @@ class _B200Extractor(FeatureExtractor):
             if input_is_torch:
                 flat = [(torch.from_numpy(x) if isinstance(x, np.ndarray) else x).squeeze() for x in items]
                 dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
+                if dt == torch.float32:  # a mixed list: PCM items get the x / 32768 an all-int16 batch gets inside the kernel
+                    flat = [t.to(torch.float32) * (1.0 / 32768.0) if t.dtype == torch.int16 else t for t in flat]
                 buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
                 out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs)
             elif self.config.dither != 0.0:  # numpy inputs with dither: device route, numpy results
                 flat = [torch.from_numpy(np.ascontiguousarray(np.asarray(x).squeeze())) for x in items]
                 dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
+                if dt == torch.float32:
+                    flat = [t.to(torch.float32) * (1.0 / 32768.0) if t.dtype == torch.int16 else t for t in flat]
                 buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
                 out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs)
                 out = out.cpu().numpy()
             else:
                 flat = [np.asarray(x).squeeze() for x in items]
                 dt = np.int16 if all(a.dtype == np.int16 for a in flat) else np.float32
+                if dt == np.float32:  # mixed list: same x / 32768 as the all-int16 route
+                    flat = [a.astype(np.float32) * np.float32(1.0 / 32768.0) if a.dtype == np.int16 else a for a in flat]
                 # pinned staging with every cut on a 4-element boundary (vector-load path of the kernels), gathered by the
                 # staging threads and double-buffered against the H2D / kernel / D2H pipeline of the C call
                 lens = [int(a.shape[0]) for a in flat]
@@ -411,26 +420,34 @@ class _B200Extractor(FeatureExtractor):
         eng = self.engine
         flat = [(torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x).squeeze() for x in samples]
         dt = torch.int16 if all(t.dtype == torch.int16 for t in flat) else torch.float32
+        if dt == torch.float32:
+            flat = [t.to(torch.float32) * (1.0 / 32768.0) if t.dtype == torch.int16 else t for t in flat]
         buf, lens, offs = pack_device(flat, eng.device, dtype=dt)
         out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs)
         return out, np.asarray(prefix, dtype=np.int64)
 
-    def extract_staged_packed(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int):
-        """`extract_batch_packed` for a batch already staged in ONE host buffer (the PCM16 ring)."""
+    def extract_staged_packed(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int,
+                              ring=None):
+        """`extract_batch_packed` for a batch already staged in ONE host buffer (the PCM16 ring; pass it as `ring` so that its
+        next `stage()` waits for this asynchronous copy)."""
         self._check_sr(sampling_rate)
         eng = self.engine
         buf = staged.to(eng.device, non_blocking=True)
+        if ring is not None:
+            ring.mark_in_flight(eng.device)
         out, prefix = eng.extract_device(self._dithered(buf), list(lens), offsets=list(offsets))
         return out, np.asarray(prefix, dtype=np.int64)
 
     def extract_staged_padded(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int,
-                              padding_value: float = LOG_EPSILON):
+                              padding_value: float = LOG_EPSILON, ring=None):
         """`extract_batch_padded` for a batch that already sits in ONE (pinned) host buffer — e.g. the int16 PCM ring of
         `lhotse_b200.pcm_staging`: one H2D copy of the raw bytes, one launch, features stay on the device."""
         self._check_sr(sampling_rate)
         eng = self.engine
         assert staged.dim() == 1 and staged.dtype in (torch.int16, torch.float32)
         buf = staged.to(eng.device, non_blocking=True)
+        if ring is not None:
+            ring.mark_in_flight(eng.device)
         out, prefix = eng.extract_device(self._dithered(buf), list(lens), offsets=list(offsets), out_mode=OUT_PADDED,
                                          pad_value=padding_value)
         return out, torch.from_numpy(np.diff(prefix)).to(torch.int64)
@@ -664,7 +681,7 @@ def from_reference_config(cfg: Any, device: str = "cuda", sampling_rate: int = 1
                  preemph_coeff=fo.preemph_coeff, window_type=fo.window_type, dither=fo.dither, snip_edges=fo.snip_edges,
                  energy_floor=cfg.energy_floor, raw_energy=cfg.raw_energy, use_energy=cfg.use_energy,
                  low_freq=mo.low_freq, high_freq=mo.high_freq, num_filters=mo.num_bins,
-                 use_fft_mag=not getattr(cfg, "use_power", True))
+                 use_fft_mag=not getattr(cfg, "use_power", True), blackman_coeff=float(getattr(fo, "blackman_coeff", 0.42)))
     else:
         raise ValueError(f"unsupported reference config type {kind}")
     if is_mfcc:

@@ -260,11 +260,12 @@ class _FamilyExtractor(FeatureExtractor):
     def extract_batch_packed(self, samples, sampling_rate: int):
         return self._inner(sampling_rate).extract_batch_packed(samples, sampling_rate)
 
-    def extract_staged_padded(self, staged, lens, offsets, sampling_rate: int, padding_value: float = LOG_EPSILON):
-        return self._inner(sampling_rate).extract_staged_padded(staged, lens, offsets, sampling_rate, padding_value=padding_value)
+    def extract_staged_padded(self, staged, lens, offsets, sampling_rate: int, padding_value: float = LOG_EPSILON, ring=None):
+        return self._inner(sampling_rate).extract_staged_padded(staged, lens, offsets, sampling_rate, padding_value=padding_value,
+                                                                ring=ring)
 
-    def extract_staged_packed(self, staged, lens, offsets, sampling_rate: int):
-        return self._inner(sampling_rate).extract_staged_packed(staged, lens, offsets, sampling_rate)
+    def extract_staged_packed(self, staged, lens, offsets, sampling_rate: int, ring=None):
+        return self._inner(sampling_rate).extract_staged_packed(staged, lens, offsets, sampling_rate, ring=ring)
 
     # log-mel energies: same statics as the reference classes (fbank.py:57-76, kaldifeat.py:196-215)
     mix = staticmethod(B200Fbank.mix)

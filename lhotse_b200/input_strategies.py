@@ -85,7 +85,7 @@ class FusedOnTheFlyFeatures:
             raise
         if sr != cuts[0].sampling_rate:
             return None
-        return self.extractor.extract_staged_padded(staged, lens, offs, sr, padding_value=LOG_EPSILON)
+        return self.extractor.extract_staged_padded(staged, lens, offs, sr, padding_value=LOG_EPSILON, ring=self._ring)
 
     def __call__(self, cuts, recording_field: Optional[str] = None):
         from lhotse.dataset.collation import collate_vectors, read_audio_from_cuts

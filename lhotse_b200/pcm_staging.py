@@ -124,6 +124,15 @@ class PcmStagingRing:
         self._pin = torch.cuda.is_available() if pin_memory is None else pin_memory
         self._buf = torch.empty(int(initial_samples), dtype=torch.int16, pin_memory=self._pin)
         self._headers = {}
+        self._in_flight = None  # CUDA event recorded after the last asynchronous H2D copy out of the ring
+
+    def mark_in_flight(self, device=None) -> None:
+        """Call right after an asynchronous (`non_blocking=True`) copy out of the ring: the next `stage()` waits for it before
+        it overwrites the buffer (the dependency used to hold only because a later pageable copy happened to synchronise)."""
+        if self._pin and torch.cuda.is_available():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            self._in_flight = ev
 
     def _header(self, path: str) -> WavPcm16:
         h = self._headers.get(path)
@@ -136,6 +145,9 @@ class PcmStagingRing:
     ALIGN = 4
 
     def stage(self, requests: Sequence[PcmRequest], executor=None) -> Tuple[torch.Tensor, List[int], List[int], int]:
+        if self._in_flight is not None:
+            self._in_flight.synchronize()
+            self._in_flight = None
         lens = [int(r.num_samples) for r in requests]
         offs, total = [], 0
         for n in lens:

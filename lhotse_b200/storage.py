@@ -223,7 +223,7 @@ def compute_and_store_features_fused(
                 if all(r is not None for r in reqs):
                     staged, lens, offs, fsr = ring.stage(reqs, executor=pool)
                     if fsr == sr:
-                        packed, prefix = extractor.extract_staged_packed(staged, lens, offs, sr)
+                        packed, prefix = extractor.extract_staged_packed(staged, lens, offs, sr, ring=ring)
             if packed is None:
                 audios, batch_cuts = read_audio_from_cuts(batch_cuts, executor=pool)
                 if not batch_cuts:
@@ -237,6 +237,7 @@ def compute_and_store_features_fused(
                     packed = host
                 packed = packed.numpy()
             keys = writer.write_batch([c.id for c in batch_cuts], packed, prefix)
+            writer.flush()  # a manifest entry must never precede its data (resume after a crash skips what the manifest lists)
             futures.append(saver.submit(_save, batch_cuts, packed, prefix, keys))
         for f in futures:
             f.result()

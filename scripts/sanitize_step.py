@@ -21,7 +21,7 @@ PLANS = [
     ("fast512 fbank", lb.B200Fbank(), 16000),
     ("fast512 mfcc+energy", lb.B200Mfcc(lb.B200MfccConfig(use_energy=True)), 16000),
     ("fast512 log-spectrogram", lb.B200LogSpectrogram(), 16000),
-    ("fast512x2 fbank", lb.B200Fbank(lb.B200FbankConfig(kernel="fast_x2")), 16000),
+    ("tc512 fbank", lb.B200Fbank(lb.B200FbankConfig(kernel="tc")), 16000),
     ("fast256 fbank40 8k", lb.B200Fbank(lb.B200FbankConfig(sampling_rate=8000, num_filters=40)), 8000),
     ("fast1024 fbank 24k", lb.B200Fbank(lb.B200FbankConfig(sampling_rate=24000)), 24000),
     ("fast400 fbank", lb.B200Fbank(lb.B200FbankConfig(round_to_power_of_two=False)), 16000),

@@ -1,44 +1,16 @@
-"""Test-only helper: make the *reference* (`/root/reference`, lhotse) importable in the build
-container, where `soundfile`, `intervaltree` and `cytoolz` are absent.
-Never used on the GPU box (the reference does not exist there) and never by the product."""
+"""Test-only helper: make the *reference* (lhotse) importable where `soundfile`, `intervaltree` and `cytoolz` are
+absent.  In the build container the reference is the read-only tree `/root/reference`; on the GPU box
+it is the archive `oracle/_ref/lhotse_ref.zip` that `oracle/make_ref.py` packs from that tree (git-ignored, travels with
+the snapshot; imported through zipimport).  Never used by the product."""
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("LHOTSE_REFERENCE_ROOT", "/root/reference")
-
-
-class _Stub(types.ModuleType):
-    def __getattr__(self, name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        return type(name, (), {})
-
-
-def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "lhotse"))
-
-
-def import_reference():
-    """Returns the imported `lhotse` package from the reference tree (or raises ImportError)."""
-    if not reference_available():
-        raise ImportError("reference tree not present")
-    for m in ("soundfile", "intervaltree", "cytoolz"):
-        if m not in sys.modules:
-            try:
-                __import__(m)
-            except Exception:
-                import importlib.machinery
-
-                stub = _Stub(m)
-                stub.__spec__ = importlib.machinery.ModuleSpec(m, None)  # keeps importlib.util.find_spec(m) working
-                sys.modules[m] = stub
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    sys.dont_write_bytecode = True
-    import lhotse  # noqa
-
-    return lhotse
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+from oracle.refimport import (REFERENCE_ROOT, REFERENCE_ZIP, import_reference, reference_available,  # noqa: E402,F401
+                              reference_kind)
 
 
 def install_librosa_standin():

@@ -36,7 +36,10 @@ def kernels_for(ext):
     """Every kernel that supports the plan is tested (generic always; fast when AUTO picks it)."""
     if ext.engine.kernel == "generic":
         return ["generic"]
-    return ["generic", "fast", "fast_x2"] if ext.plan.N == 512 else ["generic", "fast"]
+    ks = ["generic", "fast"]
+    if ext.plan.N == 512 and ext.plan.feature in ("fbank", "mfcc") and not ext.plan.use_energy:
+        ks.append("tc")
+    return ks
 
 
 @pytest.mark.parametrize("i,c,x,y", GOLD, ids=IDS)
@@ -51,7 +54,7 @@ def test_golden_vectors(i, c, x, y):
         assert ok, f"kernel={k}: {msg}"
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fast", "fast_x2"])
+@pytest.mark.parametrize("kernel", ["generic", "fast", "tc"])
 def test_ragged_batch_equals_per_cut(kernel):
     rs = np.random.RandomState(5)
     lens = [159, 160, 1599, 16000, 16001, 23456, 480, 100000, 16080]
@@ -73,7 +76,7 @@ def test_ragged_batch_equals_per_cut(kernel):
         assert b.is_cuda and np.array_equal(a, b.cpu().numpy())
 
 
-@pytest.mark.parametrize("kernel", ["generic", "fast", "fast_x2"])
+@pytest.mark.parametrize("kernel", ["generic", "fast", "tc"])
 def test_padded_mode_and_int16(kernel):
     rs = np.random.RandomState(6)
     pcm = [np.clip(rs.randn(n) * 3000, -32768, 32767).astype(np.int16) for n in (4000, 16000, 9999)]
