@@ -219,6 +219,15 @@ int b200feat_extract_host_at(b200feat_handle *h, const void *samples_host, int32
  * 4 twiddles (interleaved re,im). Returns the number of floats written or a negative code. */
 int64_t b200feat_get_table(b200feat_handle *h, int32_t which, float *out, int64_t capacity);
 
+/*
+ * Optional per-column affine fused into every kernel's epilogue: each stored value v of output column c (and the padding
+ * value of B200FEAT_OUT_PADDED rows) becomes v * scale[c] + shift[c].  With scale = 1 / std and shift = -mean / std this is
+ * lhotse's GlobalMVN (lhotse/dataset/signal_transforms.py:16-58: (features - norm_means) / norm_stds on the collated batch)
+ * without a second pass over the features.  `scale` / `shift`: F host floats each (copied); NULL, NULL switches it off.
+ * Not available for B200FEAT_WHISPER_FBANK.  Call it while no extraction of this handle is in flight.
+ */
+int b200feat_set_output_affine(b200feat_handle *h, const float *scale, const float *shift);
+
 int b200feat_get_stats(const b200feat_handle *h, b200feat_stats *out);
 
 #ifdef __cplusplus

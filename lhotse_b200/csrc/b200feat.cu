@@ -51,6 +51,7 @@ struct b200feat_handle {
   HostRing ring;
   Fast512Host fast;
   Tc512Host tc;
+  float *d_affine = nullptr;  // [2][F] output affine (b200feat_set_output_affine)
   Fast256Host fast256;
   Fast1024Host fast1024;
   Fast400Host fast400;
@@ -649,6 +650,29 @@ int64_t b200feat_get_table(b200feat_handle *h, int32_t which, float *out, int64_
     case 4: return pull(p.tw, (int64_t)p.Nc * 2);
     default: return fail(h, B200FEAT_EINVAL, "get_table: unknown table");
   }
+}
+
+int b200feat_set_output_affine(b200feat_handle *h, const float *scale, const float *shift) {
+  if (!h) return B200FEAT_EINVAL;
+  if (h->plan.whisper) return fail(h, B200FEAT_EUNSUPPORTED, "output affine: not available for whisper-fbank (its normalise pass is per cut)");
+  if (!scale || !shift) {
+    h->plan.post_scale = h->plan.post_shift = nullptr;
+    return B200FEAT_OK;
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+  const size_t bytes = (size_t)h->plan.F * sizeof(float);
+  if (!h->d_affine) {
+    CU_TRY(h, cudaMalloc((void **)&h->d_affine, 2 * bytes));
+    h->allocs.push_back(h->d_affine);
+  }
+  CU_TRY(h, cudaMemcpy(h->d_affine, scale, bytes, cudaMemcpyHostToDevice));
+  CU_TRY(h, cudaMemcpy(h->d_affine + h->plan.F, shift, bytes, cudaMemcpyHostToDevice));
+  h->plan.post_scale = h->d_affine;
+  h->plan.post_shift = h->d_affine + h->plan.F;
+  return B200FEAT_OK;
 }
 
 int b200feat_get_stats(const b200feat_handle *h, b200feat_stats *out) {

@@ -33,6 +33,8 @@ struct DevPlan {
   const float *mel_w;    // [sum len]
   const float *dct;      // [M*C]
   const float *lifter;   // [C]
+  const float *post_scale;  // [F] or nullptr: every stored value v of column c becomes v * post_scale[c] + post_shift[c]
+  const float *post_shift;  //   (b200feat_set_output_affine: a fused GlobalMVN, lhotse/dataset/signal_transforms.py:16-58)
 };
 
 // One launch's view of the ragged batch (all device pointers).
@@ -61,6 +63,12 @@ __device__ __forceinline__ float ld_sample(const void *base, int64_t i) {
   } else {
     return __ldg(reinterpret_cast<const float *>(base) + i);
   }
+}
+
+// Optional per-column affine of the kernels' epilogues.  The padding value goes through it too: the reference transform
+// sees the collated (B, T_max, F) batch, padding included (signal_transforms.py:52-57 after collation.py:506-533).
+__device__ __forceinline__ float post_affine(const DevPlan &p, int col, float v) {
+  return p.post_scale ? fmaf(v, __ldg(p.post_scale + col), __ldg(p.post_shift + col)) : v;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -269,7 +269,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
     if (p.feature == B200FEAT_SPECTROGRAM || p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int f = 0; f < nrows; ++f) {
         float *o = out + (int64_t)f * p.F;
-        if (f >= nvalid) { for (int k = lane; k < p.F; k += 32) o[k] = b.pad_value; continue; }
+        if (f >= nvalid) { for (int k = lane; k < p.F; k += 32) o[k] = post_affine(p, k, b.pad_value); continue; }
         for (int k = lane; k < p.K; k += 32) {
           float x = P[f * F1K_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
@@ -277,7 +277,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) x = (f == g) ? le[g] : x;
           }
-          o[k] = x;
+          o[k] = post_affine(p, k, x);
         }
       }
     } else {
@@ -312,7 +312,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
             float *orow = out + m + shift;
 #pragma unroll
             for (int f = 0; f < SLOTS; ++f)
-              if (f < nvalid) orow[(int64_t)f * p.F] = r[f];
+              if (f < nvalid) orow[(int64_t)f * p.F] = post_affine(p, m + shift, r[f]);
           } else {
 #pragma unroll
             for (int f = 0; f < SLOTS; ++f) mlog[f * Mpad + m] = r[f];
@@ -324,7 +324,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           float v0 = 0.f;
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) v0 = (lane == f) ? le[f] : v0;
-          out[(int64_t)lane * p.F] = v0;
+          out[(int64_t)lane * p.F] = post_affine(p, 0, v0);
         }
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
@@ -337,11 +337,11 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) acc = (f == g) ? le[g] : acc;
           }
-          out[(int64_t)f * p.F + c] = acc;
+          out[(int64_t)f * p.F + c] = post_affine(p, c, acc);
         }
       }
       for (int f = nvalid; f < nrows; ++f)
-        for (int k = lane; k < p.F; k += 32) out[(int64_t)f * p.F + k] = b.pad_value;
+        for (int k = lane; k < p.F; k += 32) out[(int64_t)f * p.F + k] = post_affine(p, k, b.pad_value);
     }
     __syncwarp();
   }

@@ -295,7 +295,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
     if (p.feature == B200FEAT_SPECTROGRAM || p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int f = 0; f < nrows; ++f) {
         float *o = out + (int64_t)f * p.F;
-        if (f >= nvalid) { for (int k = l; k < p.F; k += 8) o[k] = b.pad_value; continue; }
+        if (f >= nvalid) { for (int k = l; k < p.F; k += 8) o[k] = post_affine(p, k, b.pad_value); continue; }
         for (int k = l; k < p.K; k += 8) {
           float x = P[f * F400_PBINS + k] * (p.use_mag ? 0.5f : 0.25f);
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
@@ -303,7 +303,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
 #pragma unroll
             for (int g = 0; g < F400_SLOTS; ++g) x = (f == g) ? le[g] : x;
           }
-          o[k] = x;
+          o[k] = post_affine(p, k, x);
         }
       }
     } else {
@@ -344,7 +344,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
               float *orow = out + m + shift;
 #pragma unroll
               for (int f = 0; f < F400_SLOTS; ++f)
-                if (f < nvalid) orow[(int64_t)f * p.F] = r[f];
+                if (f < nvalid) orow[(int64_t)f * p.F] = post_affine(p, m + shift, r[f]);
             } else {
 #pragma unroll
               for (int f = 0; f < F400_SLOTS; ++f) mlog[f * Mpad + m] = r[f];
@@ -361,7 +361,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
           float v0 = 0.f;
 #pragma unroll
           for (int f = 0; f < F400_SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
-          out[(int64_t)l * p.F] = v0;
+          out[(int64_t)l * p.F] = post_affine(p, 0, v0);
         }
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
@@ -374,11 +374,11 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
 #pragma unroll
             for (int g = 0; g < F400_SLOTS; ++g) acc = (f == g) ? le[g] : acc;
           }
-          out[(int64_t)f * p.F + c] = acc;
+          out[(int64_t)f * p.F + c] = post_affine(p, c, acc);
         }
       }
       for (int f = nvalid; f < nrows; ++f)
-        for (int k = l; k < p.F; k += 8) out[(int64_t)f * p.F + k] = b.pad_value;
+        for (int k = l; k < p.F; k += 8) out[(int64_t)f * p.F + k] = post_affine(p, k, b.pad_value);
     }
     __syncwarp();
   }

@@ -467,7 +467,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
     if (p.feature == B200FEAT_SPECTROGRAM || p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int f = 0; f < nrows; ++f) {
         float *o = out + (int64_t)f * p.F;
-        if (f >= nvalid) { for (int k = l; k < p.F; k += 16) o[k] = b.pad_value; continue; }
+        if (f >= nvalid) { for (int k = l; k < p.F; k += 16) o[k] = post_affine(p, k, b.pad_value); continue; }
         for (int k = l; k < p.K; k += 16) {
           float x = P[f * PBINS + k] * (p.use_mag ? 0.5f : 0.25f);  // P holds |2X|^2 (or |2X|)
           if (p.feature == B200FEAT_LOG_SPECTROGRAM) x = log_spec_value(p, x);
@@ -475,7 +475,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) x = (f == g) ? le[g] : x;
           }
-          o[k] = x;
+          o[k] = post_affine(p, k, x);
         }
       }
     } else {
@@ -508,11 +508,11 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
             float *orow = out + m + shift;
             if (nvalid == SLOTS) {  // the common case: no per-row guards
 #pragma unroll
-              for (int f = 0; f < SLOTS; ++f) orow[(int64_t)f * p.F] = r[f];
+              for (int f = 0; f < SLOTS; ++f) orow[(int64_t)f * p.F] = post_affine(p, m + shift, r[f]);
             } else {
 #pragma unroll
               for (int f = 0; f < SLOTS; ++f)
-                if (f < nvalid) orow[(int64_t)f * p.F] = r[f];
+                if (f < nvalid) orow[(int64_t)f * p.F] = post_affine(p, m + shift, r[f]);
             }
           } else {
 #pragma unroll
@@ -524,7 +524,7 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
         if (shift && l < nvalid) { float v0 = 0.f;
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
-          out[(int64_t)l * p.F] = v0; }
+          out[(int64_t)l * p.F] = post_affine(p, 0, v0); }
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int idx = l; idx < nvalid * p.C; idx += 16) {
@@ -535,12 +535,12 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
           if (p.use_energy && c == 0) {
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) acc = (f == g) ? le[g] : acc; }
-          out[(int64_t)f * p.F + c] = acc;
+          out[(int64_t)f * p.F + c] = post_affine(p, c, acc);
         }
       }
       // padded tail rows
       for (int f = nvalid; f < nrows; ++f)
-        for (int k = l; k < p.F; k += 16) out[(int64_t)f * p.F + k] = b.pad_value;
+        for (int k = l; k < p.F; k += 16) out[(int64_t)f * p.F + k] = post_affine(p, k, b.pad_value);
     }
     __syncwarp();
   }

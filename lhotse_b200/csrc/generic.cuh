@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
     float *out = b.out + out_row * p.F;
     const int64_t T = __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut);
     if (t >= T) {  // padded tail
-      for (int c = lane; c < p.F; c += 32) out[c] = b.pad_value;
+      for (int c = lane; c < p.F; c += 32) out[c] = post_affine(p, c, b.pad_value);
       continue;
     }
     const int64_t n = __ldg(b.nsamp + cut);
@@ -185,10 +185,10 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
 
     // ---- epilogue
     if (p.feature == B200FEAT_SPECTROGRAM) {
-      for (int k = lane; k < p.K; k += 32) out[k] = (k == 0 && p.use_energy) ? le : raw[k];
+      for (int k = lane; k < p.K; k += 32) out[k] = post_affine(p, k, (k == 0 && p.use_energy) ? le : raw[k]);
     } else if (p.feature == B200FEAT_LOG_SPECTROGRAM) {
       for (int k = lane; k < p.K; k += 32)
-        out[k] = (k == 0 && p.use_energy) ? le : log_spec_value(p, raw[k]);
+        out[k] = post_affine(p, k, (k == 0 && p.use_energy) ? le : log_spec_value(p, raw[k]));
     } else {
       float *mlog = reinterpret_cast<float *>(dst);  // scratch (FFT buffer not holding the result)
       const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         const float fl = nanmax(acc, p.mel_floor);
         const float v = p.log10_mel ? log10f(fl) : logf(fl);  // whisper_fbank.py:67, librosa_fbank.py:126
         vmax = nanmax(vmax, v);
-        if (p.feature == B200FEAT_MFCC) mlog[m] = v; else out[m + shift] = v;
+        if (p.feature == B200FEAT_MFCC) mlog[m] = v; else out[m + shift] = p.whisper ? v : post_affine(p, m + shift, v);
       }
       if (p.whisper) {
         // the cut-wide maximum the normalise pass clamps against (whisper_fbank.py:68); rows past the stft's n / S
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         for (int o = 16; o > 0; o >>= 1) vmax = nanmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         if (lane == 0 && t < n / p.S) atomic_max_float(b.cut_max + cut, vmax);
       } else if (p.feature == B200FEAT_FBANK) {
-        if (shift && lane == 0) out[0] = le;
+        if (shift && lane == 0) out[0] = post_affine(p, 0, le);
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int c = lane; c < p.C; c += 32) {
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
           for (int m = 0; m < p.M; ++m) acc += mlog[m] * __ldg(p.dct + m * p.C + c);
           if (p.use_lifter) acc *= __ldg(p.lifter + c);
           if (p.use_energy && c == 0) acc = le;
-          out[c] = acc;
+          out[c] = post_affine(p, c, acc);
         }
       }
     }

@@ -62,7 +62,7 @@ EXPORTS = [
     "b200feat_last_error", "b200feat_num_frames", "b200feat_feature_dim", "b200feat_kernel_kind",
     "b200feat_meta_words", "b200feat_plan_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
     "b200feat_extract_host_at", "b200feat_desc_num_frames",
-    "b200feat_get_table", "b200feat_get_stats",
+    "b200feat_get_table", "b200feat_get_stats", "b200feat_set_output_affine",
 ]
 
 
@@ -118,6 +118,8 @@ def load_library():
         lib.b200feat_get_table.argtypes = [vp, i32, vp, i64]
         lib.b200feat_get_stats.restype = C.c_int
         lib.b200feat_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        lib.b200feat_set_output_affine.restype = C.c_int
+        lib.b200feat_set_output_affine.argtypes = [vp, vp, vp]
         if lib.b200feat_version() != 1:
             raise ImportError("libb200feat.so ABI version mismatch")
         _LIB = lib
@@ -329,6 +331,18 @@ class Engine:
             if side is not None:
                 side.shutdown(wait=True)
         return out, prefix
+
+    def set_output_affine(self, scale: Optional[np.ndarray], shift: Optional[np.ndarray]) -> None:
+        """Fuses `v * scale[c] + shift[c]` (per output column c; the padding value too) into the kernels' epilogue —
+        e.g. GlobalMVN with scale = 1 / std, shift = -mean / std.  `None, None` switches it off."""
+        if scale is None or shift is None:
+            self._check(self.lib.b200feat_set_output_affine(self._h, None, None))
+            return
+        sc = np.ascontiguousarray(scale, dtype=np.float32).reshape(-1)
+        sh = np.ascontiguousarray(shift, dtype=np.float32).reshape(-1)
+        if sc.shape[0] != self.feature_dim or sh.shape[0] != self.feature_dim:
+            raise ValueError(f"output affine needs {self.feature_dim} values per table, got {sc.shape[0]} / {sh.shape[0]}")
+        self._check(self.lib.b200feat_set_output_affine(self._h, _ptr(sc), _ptr(sh)))
 
     # ------------------------------------------------------------------ introspection
     def get_table(self, which: int) -> np.ndarray:

@@ -400,13 +400,20 @@ class _B200Extractor(FeatureExtractor):
         return out.reshape(B, T, -1), remainder
 
     # -- extras used by the fused-collation ("next") path -----------------------
+    def affine_engine(self, scale, shift) -> Engine:
+        """A second handle of the same plan whose kernels apply `v * scale[c] + shift[c]` in their epilogue (fused GlobalMVN,
+        signal_transforms.py:16-58).  Pass it as `engine=` to the padded / packed batch entry points."""
+        eng = Engine(self.plan, device=self.config.device, kernel=getattr(self.config, "kernel", "auto"))
+        eng.set_output_affine(scale, shift)
+        return eng
+
     def extract_batch_padded(self, samples: Sequence[torch.Tensor], sampling_rate: int,
-                             padding_value: float = LOG_EPSILON):
+                             padding_value: float = LOG_EPSILON, engine: Optional[Engine] = None):
         """Ragged list -> ((B, T_max, F) padded with `padding_value`, int64 frame lengths), i.e.
         `extract_batch` + `collate_matrices(padding_value=LOG_EPSILON)` (collation.py:506-533,
         input_strategies.py:441-462) in one launch, staying on the device."""
         self._check_sr(sampling_rate)
-        eng = self.engine
+        eng = engine or self.engine
         flat = [(torch.from_numpy(x) if isinstance(x, np.ndarray) else x).squeeze() for x in samples]
         buf, lens, offs = pack_device(flat, eng.device)
         out, prefix = eng.extract_device(self._dithered(buf), lens, offsets=offs, out_mode=OUT_PADDED, pad_value=padding_value)
@@ -439,11 +446,11 @@ class _B200Extractor(FeatureExtractor):
         return out, np.asarray(prefix, dtype=np.int64)
 
     def extract_staged_padded(self, staged: torch.Tensor, lens: Sequence[int], offsets: Sequence[int], sampling_rate: int,
-                              padding_value: float = LOG_EPSILON, ring=None):
+                              padding_value: float = LOG_EPSILON, ring=None, engine: Optional[Engine] = None):
         """`extract_batch_padded` for a batch that already sits in ONE (pinned) host buffer — e.g. the int16 PCM ring of
         `lhotse_b200.pcm_staging`: one H2D copy of the raw bytes, one launch, features stay on the device."""
         self._check_sr(sampling_rate)
-        eng = self.engine
+        eng = engine or self.engine
         assert staged.dim() == 1 and staged.dtype in (torch.int16, torch.float32)
         buf = staged.to(eng.device, non_blocking=True)
         if ring is not None:

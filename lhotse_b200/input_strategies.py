@@ -33,6 +33,7 @@ class FusedOnTheFlyFeatures:
         executor_type: Type = ThreadPoolExecutor,
         features_on_device: bool = True,
         pcm16_fast_path: bool = True,
+        global_mvn=None,
     ) -> None:
         if not hasattr(extractor, "extract_batch_padded"):
             raise TypeError("FusedOnTheFlyFeatures needs a lhotse_b200 extractor (extract_batch_padded)")
@@ -54,6 +55,24 @@ class FusedOnTheFlyFeatures:
         self.last_batch_route = None  # "pcm16" | "float" (introspection for tests / logs)
         self._executor_type = executor_type
         self._executor = None
+        # §8f-1: GlobalMVN (lhotse/dataset/signal_transforms.py:16-58) fused into the kernels' epilogue.  `global_mvn` is a
+        # lhotse GlobalMVN module, a dict with "norm_means" / "norm_stds", or a (means, stds) pair; the strategy then returns
+        # (features - means) / stds — padding included, exactly what GlobalMVN()(collated batch) yields — with no second pass.
+        self._mvn_engine = None
+        if global_mvn is not None:
+            import numpy as np
+
+            if hasattr(global_mvn, "norm_means"):
+                means, stds = global_mvn.norm_means, global_mvn.norm_stds
+            elif isinstance(global_mvn, dict):
+                means, stds = global_mvn["norm_means"], global_mvn["norm_stds"]
+            else:
+                means, stds = global_mvn
+            means = np.asarray(torch.as_tensor(means).detach().cpu(), dtype=np.float64)
+            stds = np.asarray(torch.as_tensor(stds).detach().cpu(), dtype=np.float64)
+            if not hasattr(extractor, "affine_engine"):
+                raise TypeError("global_mvn needs a lhotse_b200 extractor with one sampling rate (affine_engine)")
+            self._mvn_engine = extractor.affine_engine((1.0 / stds).astype(np.float32), (-means / stds).astype(np.float32))
 
     def _get_executor(self):
         if self.num_workers <= 0:
@@ -85,7 +104,8 @@ class FusedOnTheFlyFeatures:
             raise
         if sr != cuts[0].sampling_rate:
             return None
-        return self.extractor.extract_staged_padded(staged, lens, offs, sr, padding_value=LOG_EPSILON, ring=self._ring)
+        return self.extractor.extract_staged_padded(staged, lens, offs, sr, padding_value=LOG_EPSILON, ring=self._ring,
+                                                    **({"engine": self._mvn_engine} if self._mvn_engine is not None else {}))
 
     def __call__(self, cuts, recording_field: Optional[str] = None):
         from lhotse.dataset.collation import collate_vectors, read_audio_from_cuts
@@ -107,9 +127,11 @@ class FusedOnTheFlyFeatures:
                 audios[idx] = tfnm(audios[idx])
         sr = cuts[0].sampling_rate
         if all(c.sampling_rate == sr for c in cuts):
-            feats, feat_lens = self.extractor.extract_batch_padded(audios, sr, padding_value=LOG_EPSILON)
+            kw = {"engine": self._mvn_engine} if self._mvn_engine is not None else {}
+            feats, feat_lens = self.extractor.extract_batch_padded(audios, sr, padding_value=LOG_EPSILON, **kw)
         else:
             assert not self.use_batch_extract, "all cuts of a batch must share one sampling rate (or pass use_batch_extract=False)"
+            assert self._mvn_engine is None, "global_mvn needs one sampling rate per batch"
             feats, feat_lens = self._extract_mixed_rates(audios, [c.sampling_rate for c in cuts])
         if not self.features_on_device:
             feats = feats.cpu()

@@ -347,7 +347,7 @@ static void upload_problem(Problem &P, DevProblem &D) {
   CK(cudaMalloc(&D.x, P.x.size() * 4)); CK(cudaMemcpy(D.x, P.x.data(), P.x.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&D.meta, P.meta.size() * 8)); CK(cudaMemcpy(D.meta, P.meta.data(), P.meta.size() * 8, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&D.out, (size_t)P.rows * P.p.F * 4)); CK(cudaMemset(D.out, 0xff, (size_t)P.rows * P.p.F * 4));
-  CK(cudaMalloc(&D.dbg, (5 * 128 * 32 + TC_NF * TC_PP) * 4)); CK(cudaMemset(D.dbg, 0, (5 * 128 * 32 + TC_NF * TC_PP) * 4));
+  CK(cudaMalloc(&D.dbg, (2 * 128 * 32 + TC_NF * TC_PP) * 4)); CK(cudaMemset(D.dbg, 0, (2 * 128 * 32 + TC_NF * TC_PP) * 4));
   int fpt = 0;
   int rc = tc512_prepare(P.p, P.bank, D.allocs, &fpt, P.window, &D.hst);
   if (rc) { printf("tc512_prepare failed: %d\n", rc); exit(2); }
@@ -359,40 +359,29 @@ static void upload_problem(Problem &P, DevProblem &D) {
   db.out_mode = B200FEAT_OUT_PACKED; db.pad_value = 0.f;
 }
 
-template <int A1M>
 static int tc_run() {
   Problem P;
   make_problem(P, {16000, 4000, 1599, 160000, 159, 2720}, 80, 1);
   DevProblem D;
   upload_problem(P, D);
   printf("tc: %lld rows, %lld tiles, smem %zu B, blob %d B\n", (long long)P.rows, (long long)P.tiles, D.hst.smem, D.hst.t.cblob_bytes);
-  CK(cudaFuncSetAttribute(b200feat_tc512_kernel<B200FEAT_F32, 1, A1M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.hst.smem));
+  CK(cudaFuncSetAttribute(b200feat_tc512_kernel<B200FEAT_F32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.hst.smem));
   {
-    int occ = 0;
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, b200feat_tc512_kernel<B200FEAT_F32, 0, TC_A1_MODE>));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b200feat_tc512_kernel<B200FEAT_F32, 0, TC_A1_MODE>, TC_THREADS, D.hst.smem));
-    printf("tc (A1 mode %d): regs %d, static smem %zu, max dyn smem %d, occupancy %d CTAs/SM at %zu B", A1M, fa.numRegs, fa.sharedSizeBytes,
-           fa.maxDynamicSharedSizeBytes, occ, D.hst.smem);
-    for (size_t sm : {(size_t)0, (size_t)40000, (size_t)80000}) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, b200feat_tc512_kernel<B200FEAT_F32, 0, TC_A1_MODE>, TC_THREADS, sm));
-      printf(", %d at %zu", occ, sm);
-    }
-    cudaDeviceProp pr;
-    cudaGetDeviceProperties(&pr, 0);
-    printf("; regs/SM %d, smem/SM %zu, smem/block optin %zu\n", pr.regsPerMultiprocessor, pr.sharedMemPerMultiprocessor, pr.sharedMemPerBlockOptin);
+    CK(cudaFuncGetAttributes(&fa, b200feat_tc512_kernel<B200FEAT_F32, 0>));
+    printf("tc: regs %d, local %zu B, smem %zu B\n", fa.numRegs, fa.localSizeBytes, D.hst.smem);
   }
-  b200feat_tc512_kernel<B200FEAT_F32, 1, A1M><<<4, TC_THREADS, D.hst.smem>>>(P.p, D.hst.t, D.db, D.dbg);
+  b200feat_tc512_kernel<B200FEAT_F32, 1><<<4, TC_THREADS, D.hst.smem>>>(P.p, D.hst.t, D.db, D.dbg);
   cudaError_t e = cudaDeviceSynchronize();
   printf("tc kernel status: %s\n", cudaGetErrorString(e));
   if (e != cudaSuccess) return 1;
-  std::vector<float> dbg(5 * 128 * 32 + TC_NF * TC_PP), out((size_t)P.rows * 80);
+  std::vector<float> dbg(2 * 128 * 32 + TC_NF * TC_PP), out((size_t)P.rows * 80);
   CK(cudaMemcpy(dbg.data(), D.dbg, dbg.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out.data(), D.out, out.size() * 4, cudaMemcpyDeviceToHost));
-  // ---- stage checks on the first tile (cut 0, frames 0..15)
+  // ---- stage checks on the first tile (cut 0, frames 0..7)
   std::vector<double> v, Xr, Xi, E;
   double eY = 0, mY = 0, eX = 0, mX = 0, eP = 0, mP = 0;
-  for (int f = 0; f < 16; ++f) {
+  for (int f = 0; f < TC_NF; ++f) {
     ref_frame(P, 0, f, v, Xr, Xi, E);
     for (int n2 = 0; n2 < 16; ++n2)
       for (int k1 = 0; k1 <= 16; ++k1) {
@@ -401,22 +390,21 @@ static int tc_run() {
           const double a = -2.0 * M_PI * (double)((n1 * k1) % 32) / 32.0;
           yr += v[16 * n1 + n2] * cos(a); yi += v[16 * n1 + n2] * sin(a);
         }
-        const float *d = &dbg[((f / 8) * 128 + (f % 8) * 16 + n2) * 32];
+        const float *d = &dbg[(f * 16 + n2) * 32];
         const double gr = k1 == 0 ? d[0] : k1 == 16 ? d[1] : d[2 * k1], gi = (k1 == 0 || k1 == 16) ? 0.0 : d[2 * k1 + 1];
         eY = fmax(eY, fmax(fabs(gr - yr), fabs(gi - yi))); mY = fmax(mY, fmax(fabs(yr), fabs(yi)));
       }
-    for (int k1 = 0; k1 <= 16; ++k1)
+    for (int k1 = 0; k1 < 16; ++k1)
       for (int k2 = 0; k2 < 16; ++k2) {
         const int k = k1 + 32 * k2;
         if (k1 == 0 && k2 > 8) continue;
-        if (k1 == 16 && k2 > 7) continue;
         const double xr = k <= 256 ? Xr[k] : Xr[512 - k], xi = k <= 256 ? Xi[k] : -Xi[512 - k];
-        const float *d = k1 < 16 ? &dbg[2 * 128 * 32 + ((f / 8) * 128 + (f % 8) * 16 + k1) * 32] : &dbg[2 * 128 * 32 + (2 * 128 + f) * 32];
+        const float *d = &dbg[128 * 32 + (f * 16 + k1) * 32];
         eX = fmax(eX, fmax(fabs(d[2 * k2] - xr), fabs(d[2 * k2 + 1] - xi))); mX = fmax(mX, fmax(fabs(xr), fabs(xi)));
       }
     for (int k = 0; k <= 256; ++k) {
       const double pr = Xr[k] * Xr[k] + Xi[k] * Xi[k];
-      eP = fmax(eP, fabs(dbg[5 * 128 * 32 + f * TC_PP + k] - pr)); mP = fmax(mP, pr);
+      eP = fmax(eP, fabs(dbg[2 * 128 * 32 + f * TC_PP + k] - pr)); mP = fmax(mP, pr);
     }
   }
   printf("stage 1 (D1 = Y):  max err %.3e  (max |Y| %.3e, rel %.2e)\n", eY, mY, eY / mY);
@@ -447,27 +435,22 @@ static int tc_run() {
   return (bad == 0 && nanc == 0) ? 0 : 1;
 }
 
-template <int A1M>
-static int phases_main(int ncuts) {
+static int roles_main(int ncuts) {
   Problem P;
   make_problem(P, std::vector<int64_t>(ncuts, 160000), 80, 2);
   DevProblem D;
   upload_problem(P, D);
-  CK(cudaFuncSetAttribute(b200feat_tc512_kernel<B200FEAT_F32, 2, A1M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.hst.smem));
-  for (int grid : {148, 296}) {
-    CK(cudaMemset(D.dbg, 0, 64));
-    b200feat_tc512_kernel<B200FEAT_F32, 2, A1M><<<grid, TC_THREADS, D.hst.smem>>>(P.p, D.hst.t, D.db, D.dbg);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("phases: %s\n", cudaGetErrorString(e)); return 1; }
-    unsigned long long h[8];
-    CK(cudaMemcpy(h, D.dbg, 64, cudaMemcpyDeviceToHost));
-    const char *nm[7] = {"PRE", "MMA1", "INTER", "MMA2", "POWER", "MEL", "OUT"};
-    double tot = 0;
-    for (int i = 0; i < 7; ++i) tot += (double)h[i];
-    printf("phases (A1 mode %d, grid %d, %llu tiles): cycles per tile", A1M, grid, h[7]);
-    for (int i = 0; i < 7; ++i) printf("  %s %.0f", nm[i], (double)h[i] / h[7]);
-    printf("  | total %.0f (%.1f per frame)\n", tot / h[7], tot / h[7] / 16.0);
-  }
+  CK(cudaFuncSetAttribute(b200feat_tc512_kernel<B200FEAT_F32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.hst.smem));
+  CK(cudaMemset(D.dbg, 0, 128));
+  b200feat_tc512_kernel<B200FEAT_F32, 2><<<148, TC_THREADS, D.hst.smem>>>(P.p, D.hst.t, D.db, D.dbg);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("roles: %s\n", cudaGetErrorString(e)); return 1; }
+  unsigned long long h[16];
+  CK(cudaMemcpy(h, D.dbg, 128, cudaMemcpyDeviceToHost));
+  const char *nm[5] = {"INTER", "POWER", "PRE", "MEL", "ISSUE"};
+  printf("roles (%llu tiles of 8 frames): cycles per tile", h[15]);
+  for (int i = 0; i < 5; ++i) printf("  %s loop %.0f (waiting %.0f, working %.0f)", nm[i], (double)h[2 * i + 1] / h[15], (double)h[2 * i] / h[15], (double)(h[2 * i + 1] - h[2 * i]) / h[15]);
+  printf("\n");
   return 0;
 }
 
@@ -501,9 +484,9 @@ int main(int argc, char **argv) {
   const char *mode = argc > 1 ? argv[1] : "tc";
   if (!strcmp(mode, "disc")) return disc_main();
   if (!strcmp(mode, "rate")) return rate_main(argc > 2 ? atoi(argv[2]) : 0);
-  if (!strcmp(mode, "tc")) return (argc > 2 && atoi(argv[2]) == 1) ? tc_run<1>() : tc_run<0>();
+  if (!strcmp(mode, "tc")) return tc_run();
   if (!strcmp(mode, "bench")) return bench_main(argc > 2 ? atoi(argv[2]) : 2048);
-  if (!strcmp(mode, "phases")) return (argc > 2 && atoi(argv[2]) == 1) ? phases_main<1>(512) : phases_main<0>(512);
+  if (!strcmp(mode, "roles")) return roles_main(argc > 2 ? atoi(argv[2]) : 512);
   printf("unknown mode %s\n", mode);
   return 2;
 }

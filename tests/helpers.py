@@ -12,9 +12,12 @@ GOLDEN = os.path.join(HERE, "golden", "golden_v1.npz")
 
 # north_star: "within 1e-4 relative (float32)".  Element-wise that cannot hold against an fp32
 # reference whose own distance to the float64 truth reaches 8e-4 abs on log-mel values
-# (measured: tests/golden cases, see DESIGN.md "Parity tolerance"), so the gate is
-#   |ours - truth64| <= max(ATOL + RTOL*|truth64|, NOISE_X * max|ref32 - truth64| of the case)
-RTOL, ATOL, NOISE_X = 1e-4, 2e-4, 3.0
+# (measured: profiles/r2_parity_report.json, DESIGN.md "Parity tolerance"), so the gate is, per element,
+#   |ours - truth64| / tol <= max(1, NOISE_X * N(frame)),   tol = ATOL + RTOL*|truth64|
+# where N(frame) is the largest |ref32 - truth64| / tol over the element's own frame and its two neighbours: a noisy
+# frame of the reference (a near-cancelling bin, a frame at the mel floor) relaxes the bound for that neighbourhood
+# only, not for the whole case.  NOISE_X = 2 as SURVEY.md §7 asks.
+RTOL, ATOL, NOISE_X = 1e-4, 2e-4, 2.0
 
 
 def load_golden():
@@ -49,16 +52,16 @@ def _unit_tolerance(truth64, feature, use_energy, use_fft_mag):
     return truth64, ATOL + RTOL * np.abs(truth64)
 
 
-def gate(ours, ref32, truth64, feature, use_energy=False, use_fft_mag=False):
-    """Returns (ok, message).  max(err/tol) of ours must be <= max(1, NOISE_X * the same figure of
-    the fp32 reference itself)."""
+def gate_stats(ours, ref32, truth64, feature, use_energy=False, use_fft_mag=False):
+    """Everything the parity report records for one case: tolerance units of ours / of the fp32 reference against the
+    float64 truth, plain differences against the reference, and the gate's verdict."""
     ours = np.asarray(ours, dtype=np.float64)
     ref32 = np.asarray(ref32, dtype=np.float64)
     truth64 = np.asarray(truth64, dtype=np.float64)
     if ours.shape != ref32.shape:
-        return False, f"shape {ours.shape} != {ref32.shape}"
+        return {"ok": False, "msg": f"shape {ours.shape} != {ref32.shape}"}
     if not np.all(np.isfinite(ours)):
-        return False, "non-finite values"
+        return {"ok": False, "msg": "non-finite values"}
     tdom, tol = _unit_tolerance(truth64, feature, use_energy, use_fft_mag)
     to_dom = (lambda a: np.exp(a)) if feature == "log-spectrogram" else (lambda a: a)
     o, r = to_dom(ours), to_dom(ref32)
@@ -68,12 +71,36 @@ def gate(ours, ref32, truth64, feature, use_energy=False, use_fft_mag=False):
         tol[:, 0] = ATOL + RTOL * np.abs(truth64[:, 0])
     err = np.abs(o - tdom) / tol
     noise = np.abs(r - tdom) / tol
+    if err.ndim == 1:
+        err, noise = err[None, :], noise[None, :]
+    frame_noise = noise.max(axis=1)
+    nb = frame_noise.copy()  # the frame and its two neighbours
+    nb[1:] = np.maximum(nb[1:], frame_noise[:-1])
+    nb[:-1] = np.maximum(nb[:-1], frame_noise[1:])
+    limit = np.maximum(1.0, NOISE_X * nb)[:, None]
+    bad = int((err > limit).sum())
+    diff = np.abs(ours - ref32)
+    st = {
+        "ok": bool(bad == 0 and noise.max() <= 50),
+        "ours_max_units": float(err.max()), "ours_p99_units": float(np.percentile(err, 99)),
+        "ref32_max_units": float(noise.max()), "ref32_p99_units": float(np.percentile(noise, 99)),
+        "worst_ratio_to_limit": float((err / limit).max()), "bad": bad, "n": int(err.size),
+        "max_abs_diff_vs_ref32": float(diff.max()),
+        "max_rel_diff_vs_ref32": float((diff / np.maximum(np.abs(ref32), 1.0)).max()),
+    }
     if noise.max() > 50:
-        return False, f"reference itself is {noise.max():.1f} tolerance units from the float64 truth: wrong config?"
-    limit = max(1.0, NOISE_X * noise.max())
-    msg = (f"max err/tol ours={err.max():.3f} ref32={noise.max():.3f} limit={limit:.3f} "
-           f"max|ours-ref32|={np.abs(ours - ref32).max():.3e} bad={int((err > limit).sum())}/{err.size}")
-    return bool(err.max() <= limit), msg
+        st["msg"] = f"reference itself is {noise.max():.1f} tolerance units from the float64 truth: wrong config?"
+    else:
+        st["msg"] = (f"max err/tol ours={st['ours_max_units']:.3f} ref32={st['ref32_max_units']:.3f} worst err/limit={st['worst_ratio_to_limit']:.3f} "
+                     f"max|ours-ref32|={st['max_abs_diff_vs_ref32']:.3e} bad={bad}/{err.size}")
+    return st
+
+
+def gate(ours, ref32, truth64, feature, use_energy=False, use_fft_mag=False):
+    """Returns (ok, message): every element of ours within max(1, NOISE_X * neighbourhood noise of the fp32 reference)
+    tolerance units of the float64 truth (see the header)."""
+    st = gate_stats(ours, ref32, truth64, feature, use_energy, use_fft_mag)
+    return st["ok"], st["msg"]
 
 
 class OracleEngine:

@@ -17,7 +17,7 @@ def test_reference_arm_json_line():
               "cpu_baseline", "e2e", "gpu_launches"):
         assert k in line, k
     assert line["value"] > 0 and line["vs_baseline"] is None and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "h_audio/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
 

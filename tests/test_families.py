@@ -161,7 +161,7 @@ def test_gpu_torchaudio_adapters_golden(i, c, x, y):
     ext = cls(cls.config_type.from_dict(dict(c["cfg"])))
     got = ext.extract(x, 16000)
     assert isinstance(got, np.ndarray) and got.shape == y.shape
-    np.testing.assert_allclose(got, y, rtol=1e-3, atol=2e-3 if c["feature"] == "mfcc" else 5e-4)
+    np.testing.assert_allclose(got, y, rtol=1e-3, atol=5e-4)
     assert np.array_equal(ext.extract(torch.from_numpy(x), 16000), got)   # tensor in -> numpy out, same bits
     b = ext.extract_batch([torch.from_numpy(x), torch.from_numpy(x[:5000])], 16000)
     assert b[0].is_cuda and np.array_equal(b[0].cpu().numpy(), got) and b[1].shape[0] == (5000 + 80) // 160
@@ -186,7 +186,7 @@ def test_gpu_kaldifeat_adapters_agree_with_fbank_and_mfcc():
     # Kaldi energy convention (C0 <- log-energy) vs the torchaudio golden of the same settings
     i, c, x, y = next(t for t in TA_GOLD if t[1]["feature"] == "mfcc" and t[1]["cfg"]["use_energy"])
     ke = fam.B200KaldifeatMfcc(fam.B200KaldifeatMfccConfig(use_energy=True))
-    np.testing.assert_allclose(ke.extract(x, 16000), y, rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose(ke.extract(x, 16000), y, rtol=1e-3, atol=5e-4)
     # 8 kHz telephone geometry through the ms-spelled dict
     k8 = fam.B200KaldifeatFbank.config_type.from_dict({"frame_opts": {"samp_freq": 8000.0}, "mel_opts": {"num_bins": 40}})
     y8 = fam.B200KaldifeatFbank(k8).extract(xs[0][:8000], 8000)

@@ -127,15 +127,19 @@ def test_headline_size_properties():
 
 
 def test_mfcc_config3_tolerance():
-    """BASELINE config 3: Mfcc(num_ceps=13, num_mel_bins=23), gate like test_kaldi_features.py:116-122."""
+    """BASELINE config 3: Mfcc(num_ceps=13, num_mel_bins=23) at the reference's own tolerance (test/features/
+    test_kaldi_features.py:122: rtol 1e-3, atol 1e-4), on every kernel.  Measured (profiles/r2_parity_report.json): the smallest
+    atol that passes at rtol 1e-3 is 2.6e-5 (generic), 3.0e-5 (fast), 7.3e-5 (tc)."""
     torch.manual_seed(1)
     x = (0.1 * torch.randn(8, 160000)).numpy()
-    ext = make("mfcc", dict(num_ceps=13, num_mel_bins=23))
-    y = ext.extract_batch(x, 16000)
-    assert y.shape == (8, 1000, 13)
     cfg = O.OracleConfig(feature="mfcc", num_ceps=13, num_filters=23)
-    for b in range(8):
-        np.testing.assert_allclose(y[b], O.extract(x[b], cfg), rtol=1e-3, atol=2e-3)
+    refs = [O.extract(x[b], cfg) for b in range(8)]
+    for k in ("generic", "fast", "tc"):
+        ext = make("mfcc", dict(num_ceps=13, num_mel_bins=23), kernel=k)
+        y = ext.extract_batch(x, 16000)
+        assert y.shape == (8, 1000, 13)
+        for b in range(8):
+            np.testing.assert_allclose(y[b], refs[b], rtol=1e-3, atol=1e-4, err_msg=f"kernel={k}")
 
 
 def test_device_tables_roundtrip():
@@ -199,7 +203,7 @@ def test_long_recording_and_many_tiny_cuts():
         got = y[a0:a1]
         want = ref[a0 - shift:a1 - shift]
         assert got.shape == want.shape and got.shape[0] > 50
-        np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-3)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3)  # measured worst |ours - ref32| on noise: 6.8e-4 (r2_parity_report)
     lens = rs.randint(3200, 19200, size=5000)
     xs = [(0.1 * rs.randn(m)).astype(np.float32) for m in lens]
     out = ext.extract_batch(xs, 16000)
@@ -207,7 +211,7 @@ def test_long_recording_and_many_tiny_cuts():
     for i in rs.choice(5000, size=25, replace=False):
         ref = O.extract(xs[i], cfg)
         assert out[i].shape == ref.shape
-        np.testing.assert_allclose(out[i], ref, rtol=1e-4, atol=2e-3)
+        np.testing.assert_allclose(out[i], ref, rtol=1e-4, atol=1e-3)
 
 
 def test_nan_inputs_stay_local():
@@ -249,7 +253,7 @@ def test_torchaudio_family_golden(kernel, i, c, x, y):
     ext.config.kernel = kernel
     got = ext.extract(x, 16000)
     assert got.shape == y.shape and ext.engine.kernel == kernel
-    np.testing.assert_allclose(got, y, rtol=1e-3, atol=2e-3 if c["feature"] == "mfcc" else 5e-4)
+    np.testing.assert_allclose(got, y, rtol=1e-3, atol=5e-4)
 
 
 def test_dither_is_waveform_noise_from_the_device_generator():
@@ -511,3 +515,54 @@ def test_random_configs_auto_kernel_vs_oracle(i, feature, cfg):
             assert g.shape == ref.shape, (kern, g.shape, ref.shape)
             ok, msg = gate(g, ref, truth, feature, cfg["use_energy"], cfg["use_fft_mag"])
             assert ok, f"{kern}: {msg}"
+
+
+def test_tensor_core_kernel_at_headline_size():
+    """kernel="tc" (tcgen05 two-stage DFT, csrc/tc512.cuh) on BASELINE configs[1] inputs: against the register-FFT kernel
+    (two independent CUDA implementations of layers.py:151-186, :32-42, :565-578) and against the oracle on a sample of cuts;
+    deterministic, cuts independent, padded mode and MFCC epilogue included."""
+    torch.manual_seed(0)
+    B, n = 64, 160000
+    x = (0.1 * torch.randn(B, n)).cuda()
+    tc, fast = make("fbank", {}, kernel="tc"), make("fbank", {}, kernel="fast")
+    assert tc.engine.kernel == "tc" and fast.engine.kernel == "fast"
+    y = tc.extract_batch(x, 16000)
+    assert y.shape == (B, 1000, 80) and torch.isfinite(y).all()
+    assert torch.equal(y, tc.extract_batch(x, 16000))
+    perm = torch.randperm(B).cuda()
+    assert torch.equal(tc.extract_batch(x[perm], 16000), y[perm])
+    yf = fast.extract_batch(x, 16000)
+    assert torch.allclose(y, yf, rtol=1e-4, atol=5e-4), float((y - yf).abs().max())
+    cfg = O.OracleConfig()
+    for b in (0, 17, 63):
+        xb = x[b].cpu().numpy()
+        ok, msg = gate(y[b].cpu().numpy(), O.extract(xb, cfg), O.extract(xb, cfg, dtype=torch.float64), "fbank")
+        assert ok, msg
+    # ragged + padded collation in one launch
+    lens = [16000, 159, 48000, 1599, 20001]
+    xs = [x[i, :m].contiguous() for i, m in enumerate(lens)]
+    feats, flens = tc.extract_batch_padded(xs, 16000)
+    assert flens.tolist() == [(m + 80) // 160 for m in lens]
+    ref, _ = fast.extract_batch_padded(xs, 16000)
+    for i, T in enumerate(flens.tolist()):
+        assert torch.allclose(feats[i, :T], ref[i, :T], rtol=1e-4, atol=5e-4)
+        assert torch.all(feats[i, T:] == LOG_EPSILON)
+    # MFCC epilogue
+    m_tc, m_fast = make("mfcc", dict(num_ceps=13, num_mel_bins=23), kernel="tc"), make("mfcc", dict(num_ceps=13, num_mel_bins=23), kernel="fast")
+    a, b_ = m_tc.extract_batch(x[:8], 16000), m_fast.extract_batch(x[:8], 16000)
+    assert a.shape == (8, 1000, 13) and torch.allclose(a, b_, rtol=1e-3, atol=3e-4)
+
+
+@pytest.mark.parametrize("kernel", ["generic", "fast", "tc"])
+def test_views_with_a_storage_offset(kernel):
+    """`wave[1:]` is contiguous, so its data pointer is misaligned for the vector loads; the engine must not fault."""
+    rs = np.random.RandomState(9)
+    full = torch.from_numpy((0.1 * rs.randn(32001)).astype(np.float32)).cuda()
+    ext = make("fbank", {}, kernel=kernel)
+    for off in (1, 2, 3):
+        view = full[off:]
+        got = ext.extract(view, 16000)
+        want = ext.extract(view.clone(), 16000)
+        assert torch.equal(got, want)
+    pcm = (full * 20000).to(torch.int16)
+    assert torch.equal(ext.extract(pcm[1:], 16000), ext.extract(pcm[1:].clone(), 16000))

@@ -165,3 +165,35 @@ def test_config4_rank_sharded_cutset_fused_store(env, tmp_path):
     for c in allc:
         assert c.has_features and c.features.storage_type == "b200_archive" and c.features.type == "b200-fbank"
         _check(c.load_features(), c.load_audio()[0], ref_ext)
+
+
+def test_fused_global_mvn_matches_the_reference_transform(env, tmp_path):
+    """§8f-1: GlobalMVN (lhotse/dataset/signal_transforms.py:16-58) fused into the kernels' epilogue: FusedOnTheFlyFeatures(
+    global_mvn=...) against the reference module applied to the reference strategy's collated batch (padding included)."""
+    import lhotse_env
+    from lhotse.dataset.input_strategies import OnTheFlyFeatures
+    from lhotse.dataset.signal_transforms import GlobalMVN
+
+    from lhotse_b200.input_strategies import FusedOnTheFlyFeatures
+
+    lb_ex, _, _, _, _ = env
+    cuts = lhotse_env.make_cutset(tmp_path, [1.0, 2.5, 1.7, 3.0, 0.8], seed=7)
+    ext = _mk(lb_ex.B200Fbank, lb_ex.B200FbankConfig)
+    if ext.engine.kernel == "oracle":
+        pytest.skip("needs the CUDA engine (output affine lives in the kernels)")
+    mvn = GlobalMVN(80)
+    rs = np.random.RandomState(1)
+    mvn.norm_means.copy_(torch.from_numpy(rs.uniform(-12, -4, 80).astype(np.float32)))
+    mvn.norm_stds.copy_(torch.from_numpy(rs.uniform(0.5, 4.0, 80).astype(np.float32)))
+    plain, lens = OnTheFlyFeatures(ext)(cuts)
+    want = mvn(plain.cpu())
+    for kernel in ("fast", "tc", "generic"):
+        e2 = lb_ex.B200Fbank(lb_ex.B200FbankConfig(device="cuda:0", kernel=kernel))
+        got, glens = FusedOnTheFlyFeatures(e2, global_mvn=mvn)(cuts)
+        assert torch.equal(glens, lens) and got.shape == want.shape
+        ref = mvn(OnTheFlyFeatures(e2)(cuts)[0].cpu())  # the same kernel without the fused affine, then the reference module
+        torch.testing.assert_close(got.cpu(), ref, rtol=1e-5, atol=1e-5)
+        assert torch.allclose(got.cpu(), want, rtol=1e-4, atol=2e-3)
+    # the plain extractor is untouched by the strategy's private normalising handle
+    again, _ = OnTheFlyFeatures(ext)(cuts)
+    assert torch.equal(again, plain)
