@@ -436,15 +436,6 @@ def run_extras(args, torch, np, lb, lbd, Engine, dev, local, rank, world, xs, ns
         except Exception as ex:  # a secondary figure must never break the headline line
             extra[key] = {"error": repr(ex)}
 
-    dev_rate("mfcc", lb.B200MfccConfig(num_ceps=13, num_mel_bins=23, device=f"cuda:{local}"), "mfcc_13_23",
-             "BASELINE configs[2]: Mfcc(num_ceps=13, num_mel_bins=23), device-resident, CUDA events")
-    dev_rate("fbank", lb.B200FbankConfig(round_to_power_of_two=False, device=f"cuda:{local}"), "n400",
-             "Fbank-80 with round_to_power_of_two=False (N = L = 400), device-resident, CUDA events")
-    for k in ("fast", "tc"):
-        if k != args.kernel:
-            dev_rate("fbank", lb.B200FbankConfig(device=f"cuda:{local}", kernel=k), f"fbank80_kernel_{k}",
-                     f"the headline plan on kernel={k} (what AUTO did not pick), device-resident, CUDA events")
-
     # int16 PCM staging through the public API (half the H2D bytes)
     try:
         ext = lb.B200Fbank(lb.B200FbankConfig(device=f"cuda:{local}"))
@@ -466,6 +457,15 @@ def run_extras(args, torch, np, lb, lbd, Engine, dev, local, rank, world, xs, ns
                               "note": "B200Fbank.extract_batch(numpy int16 (B, n) in pinned memory): PCM widened inside the kernel"}
     except Exception as ex:
         extra["int16_e2e"] = {"error": repr(ex)}
+
+    dev_rate("mfcc", lb.B200MfccConfig(num_ceps=13, num_mel_bins=23, device=f"cuda:{local}"), "mfcc_13_23",
+             "BASELINE configs[2]: Mfcc(num_ceps=13, num_mel_bins=23), device-resident, CUDA events")
+    dev_rate("fbank", lb.B200FbankConfig(round_to_power_of_two=False, device=f"cuda:{local}"), "n400",
+             "Fbank-80 with round_to_power_of_two=False (N = L = 400), device-resident, CUDA events")
+    for k in ("fast", "tc"):
+        if k != args.kernel:
+            dev_rate("fbank", lb.B200FbankConfig(device=f"cuda:{local}", kernel=k), f"fbank80_kernel_{k}",
+                     f"the headline plan on kernel={k} (what AUTO did not pick), device-resident, CUDA events")
 
     if rank == 0:  # the reference's own op chain on CUDA tensors of the same GPU: the 'GPU baseline to beat' 
         try:

@@ -214,6 +214,16 @@ int b200feat_extract_host_at(b200feat_handle *h, const void *samples_host, int32
                              const int64_t *num_samples, const int64_t *sample_offsets, int32_t batch,
                              float *out_host, int32_t out_mode, float pad_value);
 
+/*
+ * Same, for cuts that live in SEPARATE host allocations (what `CutSet.compute_and_store_features_batch`, cut/set.py:2384, and
+ * `OnTheFlyFeatures`, dataset/input_strategies.py:441, hand to `extract_batch`: a list of arrays): `cuts[i]` points at the
+ * `num_samples[i]` samples of cut i.  The library gathers them into its pinned staging slots with a small thread pool
+ * (non-temporal stores; B200FEAT_STAGING_THREADS, default 8), every cut on a 16-byte boundary, and overlaps the gather of chunk
+ * c + 1 with the H2D / kernel / D2H of chunk c.  `out_host` as in b200feat_extract_host (pinned memory makes its copies async).
+ */
+int b200feat_extract_host_ptrs(b200feat_handle *h, const void *const *cuts, int32_t sample_dtype, const int64_t *num_samples,
+                               int32_t batch, float *out_host, int32_t out_mode, float pad_value);
+
 /* Read back a device-resident constant table (tests / NCCL-broadcast verification).
  * which: 0 window, 1 dense mel bank reconstructed from the sparse form (K x M), 2 dct, 3 lifter,
  * 4 twiddles (interleaved re,im). Returns the number of floats written or a negative code. */

@@ -5,8 +5,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <immintrin.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -28,8 +34,91 @@ struct HostRing {  // grow-only staging for b200feat_extract_host
   int64_t *h_meta = nullptr; size_t h_meta_cap = 0;  // pinned
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t meta_ready = nullptr;
+  // b200feat_extract_host_ptrs: two pinned staging slots the gather threads fill while the previous slot is on its way over PCIe
+  void *h_stage[2] = {nullptr, nullptr}; size_t h_stage_cap[2] = {0, 0};
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
   std::mutex mu;
 };
+
+// A small persistent pool for the host-side gather (memcpy-class work: it only has to keep a few memory channels busy).
+class GatherPool {
+ public:
+  explicit GatherPool(int n) : stop_(false), pending_(0) {
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~GatherPool() {
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // runs fn(i) for i in [0, n) on the pool and the calling thread; returns when all are done
+  void parallel_for(int n, const std::function<void(int)> &fn) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      fn_ = &fn; next_ = 0; total_ = n; pending_ = n;
+    }
+    cv_.notify_all();
+    run_some();
+    std::unique_lock<std::mutex> g(mu_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run_some() {
+    for (;;) {
+      int i;
+      const std::function<void(int)> *fn;
+      {
+        std::lock_guard<std::mutex> g(mu_);
+        if (!fn_ || next_ >= total_) return;
+        i = next_++; fn = fn_;
+      }
+      (*fn)(i);
+      std::lock_guard<std::mutex> g(mu_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [this] { return stop_ || (fn_ && next_ < total_); });
+        if (stop_) return;
+      }
+      run_some();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)> *fn_ = nullptr;
+  int next_ = 0, total_ = 0;
+  bool stop_;
+  int pending_;
+};
+
+// memcpy with non-temporal stores: the destination (pinned staging) is read next by the DMA engine, not by this core, so
+// bypassing the cache saves the read-for-ownership of every destination line (a third of the gather's memory traffic)
+static void stream_copy(void *dst, const void *src, size_t bytes) {
+  unsigned char *d = static_cast<unsigned char *>(dst);
+  const unsigned char *s = static_cast<const unsigned char *>(src);
+  const size_t head = std::min(bytes, (size_t)((32 - ((uintptr_t)d & 31)) & 31));
+  if (head) { memcpy(d, s, head); d += head; s += head; bytes -= head; }
+  const size_t blocks = bytes / 128;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s)), b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + 32));
+    const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + 64)), e = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(s + 96));
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(d), a); _mm256_stream_si256(reinterpret_cast<__m256i *>(d + 32), b);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(d + 64), c); _mm256_stream_si256(reinterpret_cast<__m256i *>(d + 96), e);
+    s += 128; d += 128;
+  }
+  bytes -= blocks * 128;
+  if (bytes) memcpy(d, s, bytes);
+  _mm_sfence();
+}
 
 }  // namespace
 
@@ -52,6 +141,7 @@ struct b200feat_handle {
   Fast512Host fast;
   Tc512Host tc;
   float *d_affine = nullptr;  // [2][F] output affine (b200feat_set_output_affine)
+  GatherPool *pool = nullptr;  // created on the first b200feat_extract_host_ptrs
   Fast256Host fast256;
   Fast1024Host fast1024;
   Fast400Host fast400;
@@ -335,6 +425,11 @@ void b200feat_destroy(b200feat_handle *h) {
   if (r.h_meta) cudaFreeHost(r.h_meta);
   for (auto &s : r.streams) if (s) cudaStreamDestroy(s);
   if (r.meta_ready) cudaEventDestroy(r.meta_ready);
+  for (int k = 0; k < 2; ++k) {
+    if (r.h_stage[k]) cudaFreeHost(r.h_stage[k]);
+    if (r.stage_free[k]) cudaEventDestroy(r.stage_free[k]);
+  }
+  delete h->pool;
   cudaSetDevice(prev);
   delete h;
 }
@@ -603,6 +698,124 @@ int b200feat_extract_host_at(b200feat_handle *h, const void *samples_host, int32
     CU_TRY(h, cudaMemcpyAsync(out_host + f0 * h->plan.F, r.d_out + f0 * h->plan.F,
                               (size_t)(f1 - f0) * h->plan.F * 4, cudaMemcpyDeviceToHost, st));
     b0 = b1; ++ci;
+  }
+  for (auto &s : r.streams) CU_TRY(h, cudaStreamSynchronize(s));
+  {
+    std::lock_guard<std::mutex> g(h->stats_mu);
+    h->stats.calls++; h->stats.cuts += B; h->stats.frames += tot.total_rows;
+    h->stats.samples += tot.span_samples; h->stats.kernel_launches += launches;
+  }
+  return B200FEAT_OK;
+}
+
+int b200feat_extract_host_ptrs(b200feat_handle *h, const void *const *cuts, int32_t dt, const int64_t *num_samples, int32_t B,
+                               float *out_host, int32_t out_mode, float pad_value) {
+  if (!h || !cuts || !num_samples || !out_host || B <= 0) return fail(h, B200FEAT_EINVAL, "extract_host_ptrs: bad arguments");
+  if (dt != B200FEAT_F32 && dt != B200FEAT_I16) return fail(h, B200FEAT_EINVAL, "bad sample dtype");
+  for (int i = 0; i < B; ++i)
+    if (!cuts[i] && num_samples[i] > 0) return fail(h, B200FEAT_EINVAL, "extract_host_ptrs: null cut pointer");
+  HostRing &r = h->ring;
+  std::lock_guard<std::mutex> guard(r.mu);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(h->device);
+  struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+
+  const size_t esz = dt == B200FEAT_I16 ? 2 : 4;
+  const int32_t align = dt == B200FEAT_I16 ? 8 : 4;  // every cut starts on a 16-byte boundary of the device buffer
+  const int64_t words = b200feat_plan_words(h, num_samples, B, out_mode);
+  if (words < 0) return (int)words;
+  if (r.h_meta_cap < (size_t)words) {
+    if (r.h_meta) cudaFreeHost(r.h_meta);
+    r.h_meta = nullptr; r.h_meta_cap = 0;
+    CU_TRY(h, cudaMallocHost((void **)&r.h_meta, (size_t)words * 8));
+    r.h_meta_cap = (size_t)words;
+  }
+  b200feat_batch_totals tot;
+  int rc = b200feat_plan_batch(h, num_samples, nullptr, B, align, out_mode, r.h_meta, words, &tot);
+  if (rc) return rc;
+  for (auto &s : r.streams) if (!s) CU_TRY(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  if (!r.meta_ready) CU_TRY(h, cudaEventCreateWithFlags(&r.meta_ready, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k)
+    if (!r.stage_free[k]) CU_TRY(h, cudaEventCreateWithFlags(&r.stage_free[k], cudaEventDisableTiming));
+  if (!h->pool) {
+    int nthreads = 8;
+    if (const char *e = getenv("B200FEAT_STAGING_THREADS")) nthreads = std::max(1, atoi(e));
+    h->pool = new GatherPool(nthreads - 1);  // the calling thread works too
+  }
+  auto grow = [&](void **p, size_t *cap, size_t need, bool host) -> cudaError_t {
+    if (*cap >= need) return cudaSuccess;
+    if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); }
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4;
+    cudaError_t e = host ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    if (e == cudaSuccess) *cap = want;
+    return e;
+  };
+  CU_TRY(h, grow(&r.d_samples, &r.d_samples_cap, (size_t)tot.span_samples * esz + 16, false));
+  CU_TRY(h, grow((void **)&r.d_out, &r.d_out_cap, (size_t)tot.out_floats * 4 + 16, false));
+  {
+    size_t capb = r.d_meta_cap * 8;
+    CU_TRY(h, grow((void **)&r.d_meta, &capb, (size_t)words * 8, false));
+    r.d_meta_cap = capb / 8;
+  }
+  CU_TRY(h, cudaMemcpyAsync(r.d_meta, r.h_meta, (size_t)words * 8, cudaMemcpyHostToDevice, r.streams[0]));
+  CU_TRY(h, cudaEventRecord(r.meta_ready, r.streams[0]));
+
+  const int64_t *soff = r.h_meta, *roff = r.h_meta + 2 * (int64_t)B, *toff = r.h_meta + 3 * (int64_t)B + 1;
+  const int64_t chunk_elems = (32ll << 20) / (int64_t)esz;
+  // chunk boundaries first: the staging slots must hold the largest chunk
+  std::vector<int> cb{0};
+  for (int b0 = 0; b0 < B;) {
+    int b1 = b0 + 1;
+    while (b1 < B && (soff[b1] + num_samples[b1]) - soff[b0] <= chunk_elems) ++b1;
+    cb.push_back(b1);
+    b0 = b1;
+  }
+  size_t max_bytes = 0;
+  for (size_t c = 0; c + 1 < cb.size(); ++c)
+    max_bytes = std::max(max_bytes, (size_t)((soff[cb[c + 1] - 1] + num_samples[cb[c + 1] - 1]) - soff[cb[c]]) * esz);
+  for (int k = 0; k < 2; ++k) CU_TRY(h, grow(&r.h_stage[k], &r.h_stage_cap[k], max_bytes + 64, true));
+
+  float *scratch = h->plan.whisper ? r.d_out + (tot.out_floats - B) : nullptr;
+  int launches = 0;
+  for (size_t c = 0; c + 1 < cb.size(); ++c) {
+    const int b0 = cb[c], b1 = cb[c + 1], slot = (int)(c & 1);
+    cudaStream_t st = r.streams[c % 3];
+    if (c < 3) CU_TRY(h, cudaStreamWaitEvent(st, r.meta_ready, 0));
+    if (c >= 2) CU_TRY(h, cudaEventSynchronize(r.stage_free[slot]));  // the H2D copy out of this slot (chunk c - 2) is done
+    unsigned char *stage = static_cast<unsigned char *>(r.h_stage[slot]);
+    const int64_t e0 = soff[b0], e1 = soff[b1 - 1] + num_samples[b1 - 1];
+    // gather: one task per ~1 MB piece so that long and short cuts balance over the threads
+    struct Piece { const unsigned char *src; unsigned char *dst; size_t bytes; };
+    std::vector<Piece> pieces;
+    for (int i = b0; i < b1; ++i) {
+      const unsigned char *src = static_cast<const unsigned char *>(cuts[i]);
+      unsigned char *dst = stage + (size_t)(soff[i] - e0) * esz;
+      size_t left = (size_t)num_samples[i] * esz;
+      while (left) {
+        const size_t take = std::min(left, (size_t)1 << 20);
+        pieces.push_back({src, dst, take});
+        src += take; dst += take; left -= take;
+      }
+      if (i + 1 < b1) {  // alignment gap before the next cut: defined bytes only
+        const size_t gap = (size_t)(soff[i + 1] - soff[i] - num_samples[i]) * esz;
+        if (gap) memset(stage + (size_t)(soff[i] + num_samples[i] - e0) * esz, 0, gap);
+      }
+    }
+    const std::function<void(int)> job = [&](int k) { stream_copy(pieces[k].dst, pieces[k].src, pieces[k].bytes); };
+    h->pool->parallel_for((int)pieces.size(), job);
+    CU_TRY(h, cudaMemcpyAsync((char *)r.d_samples + e0 * esz, stage, (size_t)(e1 - e0) * esz, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaEventRecord(r.stage_free[slot], st));
+    int64_t f0, f1;
+    if (out_mode == B200FEAT_OUT_PADDED) { f0 = (int64_t)b0 * tot.max_frames; f1 = (int64_t)b1 * tot.max_frames; }
+    else { f0 = roff[b0]; f1 = roff[b1]; }
+    rc = launch_range(h, r.d_samples, dt, r.d_meta, B, b0, b1, toff[b0], toff[b1], tot.max_frames, r.d_out, out_mode, pad_value, st,
+                      scratch, f1 - f0);
+    if (rc) return rc;
+    launches += h->plan.whisper ? 2 : 1;
+    CU_TRY(h, cudaMemcpyAsync(out_host + f0 * h->plan.F, r.d_out + f0 * h->plan.F, (size_t)(f1 - f0) * h->plan.F * 4,
+                              cudaMemcpyDeviceToHost, st));
   }
   for (auto &s : r.streams) CU_TRY(h, cudaStreamSynchronize(s));
   {

@@ -62,7 +62,7 @@ EXPORTS = [
     "b200feat_last_error", "b200feat_num_frames", "b200feat_feature_dim", "b200feat_kernel_kind",
     "b200feat_meta_words", "b200feat_plan_words", "b200feat_plan_batch", "b200feat_extract", "b200feat_extract_host",
     "b200feat_extract_host_at", "b200feat_desc_num_frames",
-    "b200feat_get_table", "b200feat_get_stats", "b200feat_set_output_affine",
+    "b200feat_get_table", "b200feat_get_stats", "b200feat_set_output_affine", "b200feat_extract_host_ptrs",
 ]
 
 
@@ -118,6 +118,8 @@ def load_library():
         lib.b200feat_get_table.argtypes = [vp, i32, vp, i64]
         lib.b200feat_get_stats.restype = C.c_int
         lib.b200feat_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        lib.b200feat_extract_host_ptrs.restype = C.c_int
+        lib.b200feat_extract_host_ptrs.argtypes = [vp, vp, i32, vp, i32, vp, i32, C.c_float]
         lib.b200feat_set_output_affine.restype = C.c_int
         lib.b200feat_set_output_affine.argtypes = [vp, vp, vp]
         if lib.b200feat_version() != 1:
@@ -298,8 +300,28 @@ class Engine:
 
     def extract_host_list(self, arrays: Sequence[np.ndarray], dtype=np.float32, sub_bytes: int = 64 << 20):
         """A LIST of separately allocated host waveforms -> packed (sum T_i, F) features in pinned host memory + row prefix.
-        The list is cut into sub-batches of ~`sub_bytes`; while the C call (H2D / kernel / D2H pipeline, GIL released)
-        works on sub-batch j out of one pinned staging buffer, the staging threads gather sub-batch j + 1 into the other."""
+        One C call (`b200feat_extract_host_ptrs`): the library gathers the cuts into its pinned staging slots with its own
+        thread pool (non-temporal stores) and overlaps that with the H2D / kernel / D2H pipeline; the GIL is released
+        throughout.  `B200FEAT_PY_GATHER=1` selects the round-1 route (Python staging threads) for A/B measurements."""
+        if os.environ.get("B200FEAT_PY_GATHER") != "1":
+            want = np.dtype(dtype)
+            arrs = [np.ascontiguousarray(a, dtype=want).reshape(-1) for a in arrays]
+            B = len(arrs)
+            ns = np.asarray([a.shape[0] for a in arrs], dtype=np.int64)
+            p = self.plan
+            if p.snip_edges and p.feature not in ("whisper-fbank", "librosa-fbank"):
+                Ts = np.where(ns < p.L, 0, 1 + (ns - p.L) // p.S)
+            else:
+                Ts = (ns + p.S // 2) // p.S
+            prefix = np.concatenate(([0], np.cumsum(Ts))).astype(np.int64)
+            out = torch.empty((int(prefix[-1]), self.feature_dim), dtype=torch.float32, pin_memory=torch.cuda.is_available()).numpy()
+            ptrs = (C.c_void_p * B)(*[a.ctypes.data for a in arrs])
+            rc = self.lib.b200feat_extract_host_ptrs(self._h, ptrs, DT_I16 if want == np.int16 else DT_F32, _ptr(ns), B, out.ctypes.data,
+                                                     OUT_PACKED, 0.0)
+            if rc == -5:
+                raise ValueError(self.lib.b200feat_last_error(self._h).decode())
+            self._check(rc)
+            return out, prefix
         lens = [int(a.shape[0]) for a in arrays]
         B = len(lens)
         p = self.plan

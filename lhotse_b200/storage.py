@@ -181,7 +181,7 @@ def compute_and_store_features_fused(
     register_with_lhotse()
     frame_shift = extractor.frame_shift
     cuts_writer = CutSet.open_writer(manifest_path, overwrite=overwrite)
-    sampler = SimpleCutSampler(cuts, max_duration=batch_duration)
+    sampler = SimpleCutSampler(cuts, max_duration=batch_duration, world_size=1, rank=0)  # this rank's shard already: no second split under torch.distributed
     sampler.filter(lambda cut: cut.id not in cuts_writer.ignore_ids)
     ring = PcmStagingRing() if pcm16_fast_path and hasattr(extractor, "extract_staged_packed") else None
     pool = ThreadPoolExecutor(max_workers=num_workers) if num_workers > 0 else None
@@ -206,7 +206,11 @@ def compute_and_store_features_fused(
                 cut = MonoCut(id=cut.id, start=0, duration=cut.duration, channel=0,
                               supervisions=[fastcopy(s, recording_id=cut.id, channel=0) for s in cut.supervisions],
                               features=fm, recording=None)
-            cuts_writer.write(cut, flush=True)
+            cuts_writer.write(cut, flush=False)
+        # one flush per BATCH (the reference flushes per cut, set.py:2340: with a gzip manifest every flush is a sync block);
+        # the archive was flushed before this batch was queued, so a manifest entry still never precedes its data
+        if getattr(cuts_writer, "file", None) is not None:
+            cuts_writer.file.flush()
 
     with cuts_writer, B200ArchiveWriter(storage_path, mode="w" if overwrite else "a") as writer, \
             ThreadPoolExecutor(max_workers=1) as saver:  # one background saver: deterministic manifest order

@@ -80,3 +80,62 @@ def test_numa_binding_helpers_are_safe_without_gpu():
     assert lbd.bind_host_to_gpu_numa(0) is None or isinstance(lbd.bind_host_to_gpu_numa(0), int)
     if not torch.cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def _cutset_worker(rank, world, port, q):
+    """BASELINE configs[4] at test size under a REAL process group (world size 2, gloo): the rank-sharded fused store of
+    scripts/bench_config5.py with the oracle-backed engine.  Catches what single-process tests cannot: lhotse's samplers
+    shard by the ambient process group on their own, so a shard that is split a second time loses half its cuts."""
+    import sys
+
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import refshim  # noqa: F401
+    import scripts.bench_config5 as bc
+    from helpers import attach_oracle_engine
+
+    torch.cuda.synchronize = lambda *a, **k: None
+    lbd.init_distributed(backend="gloo")
+    lb_ex = bc._ensure_lhotse()
+    orig = lb_ex.B200Fbank
+
+    class Fake(orig):
+        def __init__(self, cfg=None):
+            super().__init__(cfg)
+            attach_oracle_engine(self)
+
+        @property
+        def engine(self):
+            return self._engine
+
+    Fake.name = orig.name
+    lb_ex.B200Fbank = Fake
+    res = bc.run_cutset_job(rank, world, rank, seconds_of_audio=40.0, num_workers=0, batch_duration=25.0)
+    q.put((rank, res["cuts"], res.get("spot_check_max_abs_diff")))
+    dist.destroy_process_group()
+
+
+@pytest.mark.reference
+def test_world2_cutset_level_sharded_store():
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import refshim
+
+    if not refshim.reference_available():
+        pytest.skip("reference not present")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cutset_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [8, 8] and res[0][2] == 0.0  # 4 cuts per rank, corpus order restored, archive bit-exact
