@@ -16,8 +16,8 @@
 #include <vector>
 
 #include "common.cuh"
-#include "generic.cuh"
 #include "fast512.cuh"
+#include "generic.cuh"
 #include "tc512.cuh"
 #include "fast256.cuh"
 #include "fast1024.cuh"
@@ -175,8 +175,15 @@ int upload(b200feat_handle *h, const T *src, size_t count, const T **dst) {
 
 std::vector<int> factorize(int n) {
   std::vector<int> f;
-  while (n % 4 == 0) { f.push_back(4); n /= 4; }
-  while (n % 2 == 0) { f.push_back(2); n /= 2; }
+  // powers of two: as many radix-16 passes as possible, LAST among the power-of-two passes (their scattered stores are
+  // conflict-free once the sub-transform length Ns is >= 32), a radix-4 / radix-2 remainder first
+  int e = 0;
+  while (n % 2 == 0) { ++e; n /= 2; }
+  const int n16 = e >= 8 ? e / 4 : 0;  // below 256 points the radix-4 passes are as good
+  int rem = e - 4 * n16;
+  while (rem >= 2) { f.push_back(4); rem -= 2; }
+  if (rem == 1) f.push_back(2);
+  for (int i = 0; i < n16; ++i) f.push_back(16);
   for (int p = 3; n > 1; p += 2)
     while (n % p == 0) { f.push_back(p); n /= p; }
   return f;

@@ -294,7 +294,7 @@ class _B200Extractor(FeatureExtractor):
             if arr.dtype not in (np.float32, np.int16):
                 arr = arr.astype(np.float32)
             lens = [nmax] * B
-            if arr.nbytes >= (16 << 20) and hasattr(eng, "extract_host_list") and not torch.from_numpy(arr).is_pinned():
+            if arr.nbytes >= (16 << 20) and not torch.from_numpy(arr).is_pinned():
                 # pageable memory: the driver would bounce it through its own staging on ONE thread; gather the rows into
                 # pinned memory with the staging threads instead, double-buffered against the transfer
                 out, prefix = eng.extract_host_list(list(arr), dtype=arr.dtype)
@@ -334,11 +334,7 @@ class _B200Extractor(FeatureExtractor):
                 # pinned staging with every cut on a 4-element boundary (vector-load path of the kernels), gathered by the
                 # staging threads and double-buffered against the H2D / kernel / D2H pipeline of the C call
                 lens = [int(a.shape[0]) for a in flat]
-                if hasattr(eng, "extract_host_list"):
-                    out, prefix = eng.extract_host_list(flat, dtype=dt)
-                else:
-                    stage, lens, offs = stage_host(flat, dtype=dt)
-                    out, prefix = eng.extract_host(stage, lens, offsets=offs)
+                out, prefix = eng.extract_host_list(flat, dtype=dt)
             result = [out[prefix[i]: prefix[i + 1]] for i in range(len(lens))]
         if self._returns_cpu_tensor and input_is_torch:
             result = [r.cpu() for r in result]

@@ -140,6 +140,10 @@ class OracleEngine:
             return res, prefix
         return np.concatenate(outs, axis=0), prefix
 
+    def extract_host_list(self, arrays, dtype=np.float32, sub_bytes=0):
+        outs, prefix = self._run([np.asarray(a) for a in arrays])
+        return np.concatenate(outs, axis=0), prefix
+
     def extract_device(self, samples, num_samples, offsets=None, out_mode=0, pad_value=0.0, **kw):
         flat = samples.cpu().numpy()
         if offsets is None:

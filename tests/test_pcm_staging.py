@@ -238,14 +238,17 @@ def test_gpu_packed_batch_to_archive_roundtrip(tmp_path):
     assert np.array_equal(pa, pb) and torch.equal(a, b)
 
 
-def test_extract_host_list_pipeline_logic_with_a_recording_engine():
-    """CPU-only check of `Engine.extract_host_list` (sub-batching, double buffering, row prefix, aligned offsets): the C call
+def test_extract_host_list_pipeline_logic_with_a_recording_engine(monkeypatch):
+    """CPU-only check of the Python staging route of `Engine.extract_host_list` (`B200FEAT_PY_GATHER=1`; the default route is
+    one C call, `b200feat_extract_host_ptrs`, exercised by the `-m gpu` ragged-list tests): sub-batching, double buffering, row
+    prefix, aligned offsets.  The C call
     is replaced by a recorder that 'extracts' one row per 160 samples holding the cut's first sample, so every row of the
     result says which cut and which staging buffer content produced it."""
     import lhotse_b200.engine as E
     from lhotse_b200.plan import build_plan
     import lhotse_b200 as lb
 
+    monkeypatch.setenv("B200FEAT_PY_GATHER", "1")
     eng = E.Engine.__new__(E.Engine)
     eng.plan = build_plan("fbank", lb.B200FbankConfig())
     eng.feature_dim = 3
