@@ -423,8 +423,9 @@ def run_extras(args, torch, np, lb, lbd, Engine, dev, local, rank, world, xs, ns
     hours = B * nsamp / SR / 3600.0
     x2 = [x[: B * nsamp] for x in xs]
 
-    def dev_rate(kind, cfg, key, note):
+    def dev_rate(kind, cfg, key, note, sr=SR):
         try:
+            hours = B * nsamp / sr / 3600.0
             plan = lb.build_plan(kind, cfg)
             e = Engine(plan, device=dev, kernel=getattr(cfg, "kernel", "auto"))
             NL = _calibrate(torch, e, x2[0], lens, offs, 60.0)
@@ -463,6 +464,9 @@ def run_extras(args, torch, np, lb, lbd, Engine, dev, local, rank, world, xs, ns
              "BASELINE configs[2]: Mfcc(num_ceps=13, num_mel_bins=23), device-resident, CUDA events")
     dev_rate("fbank", lb.B200FbankConfig(round_to_power_of_two=False, device=f"cuda:{local}"), "n400",
              "Fbank-80 with round_to_power_of_two=False (N = L = 400), device-resident, CUDA events")
+    dev_rate("fbank", lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05, device=f"cuda:{local}"), "n2048_24k_50ms",
+             "Fbank-80 at 24 kHz with 50 ms frames (L = 1200, N = 2048: the fast2048 kernel; the same sample buffer read as 24 kHz "
+             "audio), device-resident, CUDA events", sr=24000)
     for k in ("fast", "tc"):
         if k != args.kernel:
             dev_rate("fbank", lb.B200FbankConfig(device=f"cuda:{local}", kernel=k), f"fbank80_kernel_{k}",

@@ -16,11 +16,12 @@
 #include <vector>
 
 #include "common.cuh"
-#include "fast512.cuh"
 #include "generic.cuh"
+#include "fast512.cuh"
 #include "tc512.cuh"
 #include "fast256.cuh"
 #include "fast1024.cuh"
+#include "fast2048.cuh"
 #include "fast400.cuh"
 
 namespace {
@@ -144,6 +145,7 @@ struct b200feat_handle {
   GatherPool *pool = nullptr;  // created on the first b200feat_extract_host_ptrs
   Fast256Host fast256;
   Fast1024Host fast1024;
+  Fast2048Host fast2048;
   Fast400Host fast400;
 };
 
@@ -175,15 +177,11 @@ int upload(b200feat_handle *h, const T *src, size_t count, const T **dst) {
 
 std::vector<int> factorize(int n) {
   std::vector<int> f;
-  // powers of two: as many radix-16 passes as possible, LAST among the power-of-two passes (their scattered stores are
-  // conflict-free once the sub-transform length Ns is >= 32), a radix-4 / radix-2 remainder first
-  int e = 0;
-  while (n % 2 == 0) { ++e; n /= 2; }
-  const int n16 = e >= 8 ? e / 4 : 0;  // below 256 points the radix-4 passes are as good
-  int rem = e - 4 * n16;
-  while (rem >= 2) { f.push_back(4); rem -= 2; }
-  if (rem == 1) f.push_back(2);
-  for (int i = 0; i < n16; ++i) f.push_back(16);
+  // radix 4 / 2 passes.  (A register radix-16 pass — a quarter of the shared-memory round trips — was measured in round 2 and
+  // changed nothing: N = 2048 98 vs 90-99 h/s, N = 512 slower; at one warp per frame and 8 warps per SM the generic kernel is
+  // bound by its instruction count and occupancy, not by the passes.  profiles/r2_bench_other_configs.jsonl)
+  while (n % 4 == 0) { f.push_back(4); n /= 4; }
+  while (n % 2 == 0) { f.push_back(2); n /= 2; }
   for (int p = 3; n > 1; p += 2)
     while (n % p == 0) { f.push_back(p); n /= p; }
   return f;
@@ -357,10 +355,11 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   const bool fast256_ok = !whisper && fast256_supported(p);
   const bool fast1024_ok = !whisper && fast1024_supported(p);
   const bool fast400_ok = fast400_supported(p);
-  const bool fast_ok = fast512_ok || fast256_ok || fast1024_ok || fast400_ok;
+  const bool fast2048_ok = !whisper && fast2048_supported(p);
+  const bool fast_ok = fast512_ok || fast256_ok || fast1024_ok || fast2048_ok || fast400_ok;
   if (desc->kernel == B200FEAT_KERNEL_FAST && !fast_ok) {
     cudaSetDevice(prev); b200feat_destroy(h);
-    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 256, 512, 1024 or frame_length = fft_length = 400");
+    return fail(nullptr, B200FEAT_EUNSUPPORTED, "fast kernels require fft_length 256, 512, 1024, 2048 or frame_length = fft_length = 400");
   }
   bool auto_tc = false;  // AUTO prefers the tensor-core kernel where it is the faster one (B200FEAT_AUTO_TC=0/1 overrides)
   if (const char *e = getenv("B200FEAT_AUTO_TC")) auto_tc = atoi(e) != 0;
@@ -404,6 +403,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
     if (h->plan.N == 256) rc = fast256_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast256);
     else if (h->plan.N == 400) rc = fast400_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast400);
     else if (h->plan.N == 1024) rc = fast1024_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast1024);
+    else if (h->plan.N == 2048) rc = fast2048_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast2048);
     else rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
     if (rc == B200FEAT_EUNSUPPORTED && desc->kernel == B200FEAT_KERNEL_AUTO) {
       h->kernel = B200FEAT_KERNEL_GENERIC;  // e.g. the plan's tables do not fit the fast kernel's shared memory
@@ -567,6 +567,9 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 1024) {
     int rc = fast1024_launch(h->plan, h->fast1024, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast1024 launch: ") + cudaGetErrorString((cudaError_t)rc));
+  } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 2048) {
+    int rc = fast2048_launch(h->plan, h->fast2048, db, dt, h->sm_count, stream);
+    if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast2048 launch: ") + cudaGetErrorString((cudaError_t)rc));
   } else if (h->kernel == B200FEAT_KERNEL_FAST) {
     int rc = fast512_launch(h->plan, h->fast, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512 launch: ") + cudaGetErrorString((cudaError_t)rc));

@@ -183,3 +183,94 @@ static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, i
   r.rows = r.rounds ? (int)(r.wdense.size() / lanes) : 0;
   return r;
 }
+
+// ---- the same bank cut into balanced work items (fast2048.cuh) -----------------------------------------------------
+// pack_mel_rounds gives every lane one whole filter, so a round costs its WIDEST filter and the last round of a bank runs with
+// idle lanes.  Here a filter wider than `T` taps is cut into pieces of at most T taps; items (filter, piece) are dealt to the
+// lanes in filter order, a round costs its longest piece, and a second pass adds the (<= a few) pieces of each filter in a fixed
+// order.  T is chosen on the host by simulating the shared-memory wavefronts of the epilogue's 128-bit loads (weights: one
+// conflict-free wavefront per quarter-warp; P: per quarter-warp the largest number of distinct addresses in one 16-byte bank
+// group), so piece offsets that spread over the bank groups win.
+struct MelItems {
+  std::vector<int> rstart;    // [rounds][lanes] first FFT bin of item q = lane + lanes*round (0 for idle lanes)
+  std::vector<int> rlen;      // [rounds]        trip count in taps (multiple of align)
+  std::vector<int> rrow;      // [rounds]        first row of the round in wdense
+  std::vector<float> wdense;  // [row / align][lane][align]
+  std::vector<int> qfirst;    // [M] first item of filter m
+  std::vector<int> qcount;    // [M] number of items (0: the filter has no taps)
+  int rounds = 0, rows = 0, items = 0, piece = 0;
+  int max_reach = 0;
+  long cost = 0;              // simulated wavefronts per frame group (slots = 2)
+};
+
+static inline MelItems pack_mel_items_T(const std::vector<float> &bank, int K, int M, float scale, int lanes, int align, int T,
+                                        bool uniform = false) {  // uniform: every round runs the full T taps
+  MelItems r;
+  r.piece = T;
+  struct Item { int m, first, len; };
+  std::vector<Item> items;
+  r.qfirst.assign(M, 0); r.qcount.assign(M, 0);
+  for (int m = 0; m < M; ++m) {
+    int f0 = -1, f1 = -1;
+    for (int k = 0; k < K; ++k)
+      if (bank[(size_t)k * M + m] != 0.f) { if (f0 < 0) f0 = k; f1 = k; }
+    r.qfirst[m] = (int)items.size();
+    if (f0 < 0) continue;
+    const int s0 = f0 / align * align, end = f1 + 1;
+    for (int a = s0; a < end; a += T) items.push_back({m, a, std::min(T, end - a)});
+    r.qcount[m] = (int)items.size() - r.qfirst[m];
+  }
+  r.items = (int)items.size();
+  r.rounds = (r.items + lanes - 1) / lanes;
+  const int alloc = std::max(r.rounds, 1);
+  r.rstart.assign(alloc * lanes, 0); r.rlen.assign(alloc, 0); r.rrow.assign(alloc, 0);
+  for (int j = 0; j < r.rounds; ++j) {
+    int mx = 0;
+    for (int l = 0; l < lanes; ++l) {
+      const int q = l + lanes * j;
+      if (q < r.items) { r.rstart[q] = items[q].first; mx = std::max(mx, items[q].len); }
+    }
+    mx = uniform ? T : (mx + align - 1) / align * align;
+    for (int l = 0; l < lanes; ++l) r.max_reach = std::max(r.max_reach, r.rstart[j * lanes + l] + mx);
+    r.rlen[j] = mx;
+    r.rrow[j] = (int)(r.wdense.size() / lanes);
+    for (int g = 0; g < mx; g += align) {
+      for (int l = 0; l < lanes; ++l)
+        for (int e = 0; e < align; ++e) {
+          const int q = l + lanes * j, i = g + e;
+          r.wdense.push_back((q < r.items && i < items[q].len) ? scale * bank[(size_t)(items[q].first + i) * M + items[q].m] : 0.f);
+        }
+      // simulated cost of this trip: weights 4 wavefronts per 32 lanes, P loads per quarter-warp
+      long wf = 0;
+      for (int q0 = 0; q0 < lanes; q0 += 8) {
+        int distinct[8][8], cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int l = q0; l < q0 + 8 && l < lanes; ++l) {
+          const int a = (r.rstart[j * lanes + l] + g) / 4, bg = a & 7;
+          bool seen = false;
+          for (int c = 0; c < cnt[bg]; ++c) seen |= distinct[bg][c] == a;
+          if (!seen) distinct[bg][cnt[bg]++] = a;
+        }
+        int worst = 1;
+        for (int bg = 0; bg < 8; ++bg) worst = std::max(worst, cnt[bg]);
+        wf += worst;
+      }
+      r.cost += lanes / 8 + 2 * wf;
+    }
+  }
+  if (r.wdense.empty()) r.wdense.assign(lanes * align, 0.f);
+  r.rows = r.rounds ? (int)(r.wdense.size() / lanes) : 0;
+  return r;
+}
+
+static inline MelItems pack_mel_items(const std::vector<float> &bank, int K, int M, float scale, int lanes = 32, int align = 4) {
+  MelItems best;
+  bool have = false;
+  for (int T = 2 * align; T <= 1024; T += align) {
+    MelItems c = pack_mel_items_T(bank, K, M, scale, lanes, align, T);
+    if (c.rounds > 12) continue;  // the second pass keeps rounds * lanes partial sums per frame in shared memory
+    if (!have || c.cost < best.cost) { best = c; have = true; }
+    if (c.items == 0 || c.piece >= K) break;
+  }
+  if (!have) best = pack_mel_items_T(bank, K, M, scale, lanes, align, (K + align - 1) / align * align);
+  return best;
+}

@@ -56,6 +56,9 @@ struct Fast512Tables {  // derived once per handle
 
 __device__ __forceinline__ unsigned f512_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+// (F512_HD: the pure arithmetic helpers also compile for the host, where scripts/micro/f2k_host_check.cu runs the FFT
+// stages of fast2048.cuh lane by lane against a float64 DFT)
+#define F512_HD __host__ __device__ __forceinline__
 // Complex arithmetic on the (re, im) register pair with sm_100 packed-FP32 instructions.  SASS FADD2/FMUL2/FFMA2
 // take operand modifiers that swap the halves and flip one sign (`R.F32x2.LO_HI.NP`), so multiplying by -i / +i is
 // free inside the consuming add, and a complex multiply is FMUL2 + FFMA2 (2 issue slots instead of 4).  The FP32-pipe
@@ -63,28 +66,28 @@ __device__ __forceinline__ unsigned f512_smem_u32(const void *p) { return (unsig
 #ifndef F512_PACKED
 #define F512_PACKED 1
 #endif
-__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
-#if F512_PACKED
+F512_HD float2 f2add(float2 a, float2 b) {
+#if F512_PACKED && defined(__CUDA_ARCH__)
   return __fadd2_rn(a, b);
 #else
   return make_float2(a.x + b.x, a.y + b.y);
 #endif
 }
-__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
-#if F512_PACKED
+F512_HD float2 f2sub(float2 a, float2 b) {
+#if F512_PACKED && defined(__CUDA_ARCH__)
   return __fadd2_rn(a, make_float2(-b.x, -b.y));
 #else
   return make_float2(a.x - b.x, a.y - b.y);
 #endif
 }
-__device__ __forceinline__ float2 f2mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
-__device__ __forceinline__ float2 f2pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
-__device__ __forceinline__ float2 f2conj(float2 a) { return make_float2(a.x, -a.y); }
+F512_HD float2 f2mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+F512_HD float2 f2pi(float2 a) { return make_float2(-a.y, a.x); }   // a * (+i)
+F512_HD float2 f2conj(float2 a) { return make_float2(a.x, -a.y); }
 #ifndef F512_PACKED_MUL
 #define F512_PACKED_MUL 0
 #endif
-__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {  // complex product a * b
-#if F512_PACKED_MUL
+F512_HD float2 f2mul(float2 a, float2 b) {  // complex product a * b
+#if F512_PACKED_MUL && defined(__CUDA_ARCH__)
   return __ffma2_rn(f2pi(a), make_float2(b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
 #else
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -92,7 +95,7 @@ __device__ __forceinline__ float2 f2mul(float2 a, float2 b) {  // complex produc
 }
 
 // forward 4-point DFT, in place, natural order: 8 complex adds (the two rotations by -/+ i ride on operand modifiers)
-__device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+F512_HD void dft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
   const float2 s02 = f2add(a0, a2), d02 = f2sub(a0, a2);
   const float2 s13 = f2add(a1, a3), d13 = f2sub(a1, a3);
   a0 = f2add(s02, s13);
@@ -111,15 +114,15 @@ __device__ __forceinline__ void dft4(float2 &a0, float2 &a1, float2 &a2, float2 
 #ifndef F512_R2TRICK
 #define F512_R2TRICK 1
 #endif
-__device__ __forceinline__ float2 f2mul_w8_1(float2 a) {
-#if F512_R2TRICK && F512_PACKED
+F512_HD float2 f2mul_w8_1(float2 a) {
+#if F512_R2TRICK && F512_PACKED && defined(__CUDA_ARCH__)
   return __fmul2_rn(f2add(a, f2mi(a)), make_float2(F512_R2, F512_R2));
 #else
   return f2mul(a, make_float2(F512_R2, -F512_R2));
 #endif
 }
-__device__ __forceinline__ float2 f2mul_w8_3(float2 a) {
-#if F512_R2TRICK && F512_PACKED
+F512_HD float2 f2mul_w8_3(float2 a) {
+#if F512_R2TRICK && F512_PACKED && defined(__CUDA_ARCH__)
   return __fmul2_rn(f2add(a, f2pi(a)), make_float2(-F512_R2, -F512_R2));
 #else
   return f2mul(a, make_float2(-F512_R2, -F512_R2));
@@ -127,7 +130,7 @@ __device__ __forceinline__ float2 f2mul_w8_3(float2 a) {
 }
 
 // forward 16-point DFT in registers (radix 4x4).  Input v[n]; output X[k] lands in v[4*(k&3) + (k>>2)].
-__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+F512_HD void dft16(float2 (&v)[16]) {
 #pragma unroll
   for (int b = 0; b < 4; ++b) dft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
   // v[4c + b] = y[b][c]; twiddle by W16^(b*c), W16^m = (cos(pi m/8), -sin(pi m/8))

@@ -6,7 +6,6 @@
 // framing of :727-772, with no HBM intermediates: 4*S bytes read, 4*F bytes written per frame.
 #pragma once
 #include "common.cuh"
-#include "fast512.cuh"  // dft16: the register radix-16 butterfly
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -42,24 +41,6 @@ __device__ __forceinline__ void stockham_pass(const float2 *__restrict__ src, fl
       dst[o + Ns] = make_float2(b.x + d.x, b.y + d.y);
       dst[o + 2 * Ns] = make_float2(a.x - c.x, a.y - c.y);
       dst[o + 3 * Ns] = make_float2(b.x - d.x, b.y - d.y);
-    }
-  } else if (R == 16) {
-    // register radix-16 butterfly (4 x 4, the one of the N = 512 kernel): a power-of-two plan needs a quarter of the passes of
-    // radix 4, i.e. a quarter of the shared-memory round trips (N = 2048: 4, 16, 16 instead of five radix-4 passes)
-    for (int j = lane; j < nb; j += 32) {
-      const int k = pow2 ? (j & msk) : j % Ns;
-      float2 v[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) v[r] = src[j + r * nb];
-      if (k != 0) {
-        const int ti = k * tstep;
-#pragma unroll
-        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(tw + r * ti));
-      }
-      dft16(v);
-      const int o = (pow2 ? (j >> sh) : j / Ns) * Ns * 16 + k;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) dst[o + q * Ns] = v[F512_OUT(q)];
     }
   } else if (R == 2) {
     for (int j = lane; j < nb; j += 32) {

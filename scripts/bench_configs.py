@@ -86,12 +86,15 @@ def main():
         ("fbank80 24k N=1024 (fast1024)", lb.B200FbankConfig(sampling_rate=24000), 24000),
         ("fbank80 22.05k N=1024 (fast1024)", lb.B200FbankConfig(sampling_rate=22050), 22050),
         ("fbank80 24k N=1024 forced generic", lb.B200FbankConfig(sampling_rate=24000, kernel="generic"), 24000),
-        ("fbank80 24k 50ms N=2048", lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05), 24000),
+        ("fbank80 24k 50ms N=2048 (fast2048)", lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05), 24000),
+        ("fbank80 44.1k N=2048 (fast2048)", lb.B200FbankConfig(sampling_rate=44100), 44100),
+        ("fbank80 48k N=2048 (fast2048)", lb.B200FbankConfig(sampling_rate=48000), 48000),
+        ("fbank80 24k 50ms N=2048 forced generic", lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05, kernel="generic"), 24000),
         ("fbank80 16k N=512 forced generic", lb.B200FbankConfig(kernel="generic"), 16000),
     ):
         eng = Engine(lb.build_plan("fbank", cfg), device=dev, kernel=getattr(cfg, "kernel", "auto"))
         nn = 10 * sr
-        Bg = 256
+        Bg = 256 if sr <= 24000 else 128
         xg = x[: Bg * nn]
         lg, og = [nn] * Bg, [i * nn for i in range(Bg)]
         t_dev, _, tot = time_device(eng, xg, lg, og, reps=5)

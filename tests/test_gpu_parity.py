@@ -375,6 +375,56 @@ def test_fast1024_kernel_vs_oracle(feature, cfg, variant, monkeypatch):
             assert np.all(fcpu[i, g.shape[0]:] == np.float32(LOG_EPSILON))
 
 
+@pytest.mark.parametrize("variant", ["0", "3"])  # {11 warps, 2 frames per warp} and {14, 1}
+@pytest.mark.parametrize("feature,cfg", [
+    ("fbank", dict(sampling_rate=24000, frame_length=0.05)),                 # L = 1200, S = 240 (test_cut_consistency.py:77-105)
+    ("fbank", dict(sampling_rate=44100)),                                    # L = 1102, S = 441 (odd: every other frame unaligned)
+    ("fbank", dict(sampling_rate=48000, num_filters=128, use_energy=True)),  # L = 1200, S = 480
+    ("fbank", dict(sampling_rate=48000, use_fft_mag=True, window_type="hanning", preemph_coeff=0.0, snip_edges=True)),
+    ("mfcc", dict(sampling_rate=44100, num_ceps=20, num_filters=40)),
+    ("mfcc", dict(sampling_rate=48000, use_energy=True)),
+    ("spectrogram", dict(sampling_rate=44100)),
+    ("log-spectrogram", dict(sampling_rate=48000, use_energy=True)),
+    ("fbank", dict(sampling_rate=16000, frame_length=0.128, frame_shift=0.032)),  # L = N = 2048, S = 512
+    ("fbank", dict(sampling_rate=32000, frame_length=0.05, raw_energy=False, use_energy=True)),  # L = 1600 (run-time length)
+])
+def test_fast2048_kernel_vs_oracle(feature, cfg, variant, monkeypatch):
+    """The N = 2048 fast kernel (44.1 / 48 kHz with 25 ms frames, 24 kHz with 50 ms frames, every plan with 1024 < L <= 2048),
+    two launch shapes, against the oracle and the generic kernel on ragged lengths, plus int16 staging and the padded mode."""
+    monkeypatch.setenv("B200FEAT_FAST2048_VARIANT", variant)
+    sr = cfg["sampling_rate"]
+    ext = make(feature, cfg, kernel="fast")
+    assert ext.engine.kernel == "fast" and ext.plan.N == 2048
+    gen = make(feature, cfg, kernel="generic")
+    rs = np.random.RandomState(11)
+    S, L = ext.plan.S, ext.plan.L
+    lens = [L, L + 1, 10 * S - 1, 10 * S + S // 2, 10 * S + S // 2 - 1, 44100, 48003, 120000, 333 * S]
+    xs = [(0.1 * rs.randn(m)).astype(np.float32) for m in lens]
+    xs[3][: len(xs[3]) // 2] *= 1e-4
+    got = ext.extract_batch(xs, sr)
+    ocfg = oracle_cfg(feature, cfg)
+    for x, g in zip(xs, got):
+        ref = O.extract(x, ocfg)
+        truth = O.extract(x, ocfg, dtype=torch.float64)
+        assert g.shape == ref.shape
+        ok, msg = gate(g, ref, truth, feature, cfg.get("use_energy", False), cfg.get("use_fft_mag", False))
+        assert ok, msg
+    for a, b_ in zip(got, gen.extract_batch(xs, sr)):
+        np.testing.assert_allclose(a, b_, rtol=2e-4, atol=5e-4 if feature != "spectrogram" else 4e-3)
+    if feature == "fbank" and not cfg.get("use_energy"):
+        pcm = [np.clip(x * 32768, -32768, 32767).astype(np.int16) for x in xs]
+        i16 = ext.extract_batch(pcm, sr)
+        f32 = ext.extract_batch([q.astype(np.float32) / 32768.0 for q in pcm], sr)
+        for a, b_ in zip(i16, f32):
+            assert np.array_equal(a, b_)
+        feats, flens = ext.extract_batch_padded([torch.from_numpy(x) for x in xs], sr)
+        assert feats.shape[0] == len(xs) and flens.tolist() == [g.shape[0] for g in got]
+        fcpu = feats.cpu().numpy()
+        for i, g in enumerate(got):
+            assert np.array_equal(fcpu[i, : g.shape[0]], g)
+            assert np.all(fcpu[i, g.shape[0]:] == np.float32(LOG_EPSILON))
+
+
 from helpers import load_golden_stream  # noqa: E402
 
 STREAM = load_golden_stream()
