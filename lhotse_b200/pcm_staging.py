@@ -19,6 +19,8 @@ from __future__ import annotations
 import math
 import os
 import struct
+import threading
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -34,6 +36,49 @@ class NotPcm16Wav(ValueError):
     """The file is not a little-endian RIFF/WAVE file with 16-bit integer PCM samples."""
 
 
+class _FdCache:
+    """A few read-only descriptors kept open across cuts (a corpus job reads thousands of cuts out of the same recordings:
+    one open + close per cut costs as much as the read itself).  Reads use `os.preadv`, which carries its own offset, so
+    threads share a descriptor; an entry is dropped when the file's (size, mtime) no longer match."""
+
+    def __init__(self, capacity: int = 64):
+        self._lock = threading.Lock()
+        self._fds: "OrderedDict[str, Tuple[int, Tuple[int, int]]]" = OrderedDict()
+        self._capacity = capacity
+
+    def get(self, path: str, stamp: Tuple[int, int]) -> int:
+        with self._lock:
+            ent = self._fds.get(path)
+            if ent is not None and ent[1] == stamp:
+                self._fds.move_to_end(path)
+                return ent[0]
+            if ent is not None:
+                os.close(ent[0])
+                del self._fds[path]
+            fd = os.open(path, os.O_RDONLY)
+            self._fds[path] = (fd, stamp)
+            while len(self._fds) > self._capacity:
+                _, (old, _) = self._fds.popitem(last=False)
+                os.close(old)
+            return fd
+
+    def clear(self) -> None:
+        with self._lock:
+            for fd, _ in self._fds.values():
+                os.close(fd)
+            self._fds.clear()
+
+
+_FDS = _FdCache()
+_HEADERS: "OrderedDict[str, Tuple[Tuple[int, int], object]]" = OrderedDict()  # path -> ((size, mtime_ns), WavPcm16 | exception)
+_HEADERS_LOCK = threading.Lock()
+
+
+def _stamp(path: str) -> Tuple[int, int]:
+    st = os.stat(path)
+    return (st.st_size, st.st_mtime_ns)
+
+
 @dataclass(frozen=True)
 class WavPcm16:
     path: str
@@ -41,6 +86,32 @@ class WavPcm16:
     channels: int
     num_samples: int  # per channel
     data_offset: int  # byte offset of the first sample in the file
+    stamp: Tuple[int, int] = (0, 0)  # (file size, mtime in ns) when the header was parsed
+
+    @staticmethod
+    def open_cached(path: str) -> "WavPcm16":
+        """`open` with the parsed header remembered per path for as long as the file's size and mtime stay the same (one
+        `stat` per call instead of open + parse + close); a file that is not 16-bit PCM is remembered too."""
+        path = str(path)
+        stamp = _stamp(path)
+        with _HEADERS_LOCK:
+            ent = _HEADERS.get(path)
+            if ent is not None and ent[0] == stamp:
+                _HEADERS.move_to_end(path)
+                if isinstance(ent[1], Exception):
+                    raise ent[1]
+                return ent[1]
+        try:
+            h = WavPcm16.open(path)
+        except NotPcm16Wav as e:
+            h = e
+        with _HEADERS_LOCK:
+            _HEADERS[path] = (stamp, h)
+            while len(_HEADERS) > 65536:
+                _HEADERS.popitem(last=False)
+        if isinstance(h, Exception):
+            raise h
+        return h
 
     @staticmethod
     def open(path: str) -> "WavPcm16":
@@ -76,7 +147,9 @@ class WavPcm16:
                     avail = os.fstat(f.fileno()).st_size - off
                     if size == 0xFFFFFFFF or size > avail:  # streamed / truncated files: trust the file size
                         size = avail
-                    return WavPcm16(path=str(path), sampling_rate=sr, channels=ch, num_samples=size // (2 * ch), data_offset=off)
+                    st = os.fstat(f.fileno())
+                    return WavPcm16(path=str(path), sampling_rate=sr, channels=ch, num_samples=size // (2 * ch), data_offset=off,
+                                    stamp=(st.st_size, st.st_mtime_ns))
                 else:
                     f.seek(size + (size & 1), os.SEEK_CUR)
 
@@ -89,21 +162,21 @@ class WavPcm16:
         if not (0 <= channel < self.channels):
             raise ValueError(f"{self.path}: channel {channel} of {self.channels}")
         assert dst.dtype == np.int16 and dst.ndim == 1 and dst.flags.c_contiguous
-        with open(self.path, "rb", buffering=0) as f:
-            f.seek(self.data_offset + 2 * self.channels * first_sample)
-            if self.channels == 1:
-                view = memoryview(dst).cast("B")
-                got = 0
-                while got < len(view):
-                    k = f.readinto(view[got:])
-                    if not k:
-                        raise IOError(f"{self.path}: short read")
-                    got += k
-            else:
-                raw = np.frombuffer(f.read(2 * self.channels * n), dtype="<i2")
-                if raw.size != self.channels * n:
-                    raise IOError(f"{self.path}: short read")
-                dst[:] = raw.reshape(n, self.channels)[:, channel]
+        fd = _FDS.get(self.path, self.stamp)  # shared descriptor; preadv carries its own offset
+        pos = self.data_offset + 2 * self.channels * first_sample
+        if self.channels == 1:
+            view = memoryview(dst).cast("B")
+        else:
+            raw = np.empty(self.channels * n, dtype="<i2")
+            view = memoryview(raw).cast("B")
+        got = 0
+        while got < len(view):
+            k = os.preadv(fd, [view[got:]], pos + got)
+            if not k:
+                raise IOError(f"{self.path}: short read")
+            got += k
+        if self.channels != 1:
+            dst[:] = raw.reshape(n, self.channels)[:, channel]
         return n
 
 
@@ -137,7 +210,7 @@ class PcmStagingRing:
     def _header(self, path: str) -> WavPcm16:
         h = self._headers.get(path)
         if h is None:
-            h = self._headers[path] = WavPcm16.open(path)
+            h = self._headers[path] = WavPcm16.open_cached(path)
             if len(self._headers) > 65536:
                 self._headers.clear()
         return h
@@ -167,11 +240,18 @@ class PcmStagingRing:
             srs.add(h.sampling_rate)
             h.read_into(view[offs[i]: offs[i] + lens[i]], r.first_sample, r.channel)
 
-        if executor is None:
+        workers = getattr(executor, "_max_workers", 1) if executor is not None else 1
+        if executor is None or workers <= 1 or len(requests) < 2 * workers:
             for i in range(len(requests)):
                 one(i)
-        else:
-            list(executor.map(one, range(len(requests))))
+        else:  # one task per worker over a contiguous share of the batch (a task per cut costs more than the read it wraps)
+            step = (len(requests) + workers - 1) // workers
+
+            def share(a):
+                for i in range(a, min(a + step, len(requests))):
+                    one(i)
+
+            list(executor.map(share, range(0, len(requests), step)))
         if len(srs) != 1:
             raise ValueError(f"one sampling rate per batch expected, got {sorted(srs)}")
         return self._buf[:total], lens, offs, srs.pop()
@@ -191,7 +271,7 @@ def pcm16_request_for_cut(cut) -> Optional[PcmRequest]:
     if not isinstance(ch, int) or ch not in sources[0].channels:
         return None
     try:
-        h = WavPcm16.open(str(sources[0].source))
+        h = WavPcm16.open_cached(str(sources[0].source))
     except (NotPcm16Wav, OSError):
         return None
     if h.sampling_rate != cut.sampling_rate or h.channels != len(sources[0].channels):

@@ -64,7 +64,7 @@ def _write_recording(path, seconds, seed):
     return n
 
 
-def run_cutset_job(rank, world, local, seconds_of_audio=3600.0, cut_seconds=10.0, num_workers=4, batch_duration=2000.0, keep=False):
+def run_cutset_job(rank, world, local, seconds_of_audio=3600.0, cut_seconds=10.0, num_workers=8, batch_duration=2000.0, keep=False):
     import numpy as np
     import torch
 
@@ -190,7 +190,7 @@ def run_onthefly_job(local, seconds_of_audio=2400.0, max_duration=600.0, num_buc
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--hours-per-rank", type=float, default=1.0)
-    ap.add_argument("--num-workers", type=int, default=4)
+    ap.add_argument("--num-workers", type=int, default=8)
     ap.add_argument("--batch-duration", type=float, default=2000.0)
     args = ap.parse_args()
     import torch

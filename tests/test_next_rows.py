@@ -174,6 +174,79 @@ def test_archive_backend_and_fused_store(env, tmp_path):
     assert len(list(again)) == len(cuts) and not calls
 
 
+def test_fused_store_manifest_lines_pipeline_and_failures(env, tmp_path, monkeypatch):
+    """The fused store writes its manifest lines itself (one write per batch): every line must be the JSON of the cut's own
+    `to_dict()`; the three-stage pipeline and the sequential mode give byte-identical manifests and archives; an exception in
+    any stage surfaces in the caller and leaves no thread behind."""
+    import gzip
+    import json
+    import threading
+
+    from helpers import attach_oracle_engine
+    from lhotse import Recording
+    from lhotse.features.base import Features
+    from lhotse.utils import fastcopy
+
+    from lhotse_b200.storage import _ManifestLines, compute_and_store_features_fused
+
+    cuts, lb_ex, root = env
+    lines = _ManifestLines()
+    cl = list(cuts)
+    variants = [cl[0], fastcopy(cl[1], custom={"dataloading_info": {"rank": 0, "world_size": 1, "worker_id": None}}),
+                fastcopy(cl[2], custom={"note": "x", "nested": {"a": [1, 2.5, None]}}),
+                fastcopy(cl[3], custom={"other": cl[3].recording})]  # a Recording in `custom`: the generic path
+    for c in variants:
+        fm = Features(start=c.start, duration=c.duration, type="b200-fbank", num_frames=123, num_features=80, frame_shift=0.01,
+                      sampling_rate=c.sampling_rate, channels=c.channel, storage_type="b200_archive", storage_path="/a/b.b200feat",
+                      storage_key="0,123,80", recording_id=c.recording_id)
+        want = fastcopy(c, features=fm).to_dict()
+        got = lines.cut_dict(c, fm)
+        assert got == want and list(got) == list(want) and json.dumps(got) == json.dumps(want)
+        assert list(got["features"]) == list(want["features"])
+
+    ext = attach_oracle_engine(lb_ex.B200Fbank())
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200FEAT_STORE_PIPELINE", mode)
+        compute_and_store_features_fused(cuts, ext, root / f"pipe{mode}" / "store", manifest_path=root / f"pipe{mode}.jsonl.gz",
+                                         batch_duration=4.0, num_workers=2, overwrite=True)
+        with gzip.open(root / f"pipe{mode}.jsonl.gz", "rt") as f:
+            outs[mode] = f.read().replace(f"pipe{mode}", "pipeX")
+        assert (root / f"pipe{mode}" / "store.b200feat").read_bytes() == (root / "pipe0" / "store.b200feat").read_bytes()
+    assert outs["0"] == outs["1"] and outs["0"].count("\n") == len(cl)
+
+    class Boom(RuntimeError):
+        pass
+
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B200FEAT_STORE_PIPELINE", mode)
+        n = [0]
+        orig = ext.extract_staged_packed
+
+        def flaky(*a, **k):
+            n[0] += 1
+            if n[0] == 2:
+                raise Boom("second batch")
+            return orig(*a, **k)
+
+        ext.extract_staged_packed = flaky
+        before = threading.active_count()
+        try:
+            import pytest as _pt
+
+            with _pt.raises(Boom):
+                compute_and_store_features_fused(cuts, ext, root / f"boom{mode}", manifest_path=root / f"boom{mode}.jsonl.gz",
+                                                 batch_duration=4.0, num_workers=2, overwrite=True)
+        finally:
+            ext.extract_staged_packed = orig
+        assert threading.active_count() <= before
+        # what reached the manifest before the failure is loadable and resumable
+        done = compute_and_store_features_fused(cuts, ext, root / f"boom{mode}", manifest_path=root / f"boom{mode}.jsonl.gz",
+                                                batch_duration=4.0, num_workers=2)
+        assert [c.id for c in done] == [c.id for c in cl]
+        assert all(c.load_features().shape == (c.num_frames, 80) for c in done)
+
+
 def test_fused_on_the_fly_mixed_sampling_rates_and_family_adapters(env, tmp_path):
     """`use_batch_extract=False` (reference: sequential `extract` so that sampling rates may differ, input_strategies.py:447-459):
     here one padded extraction per sampling rate, through an extractor that takes the rate per call (torchaudio family)."""
