@@ -540,7 +540,7 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cutset", action="store_true")
-    ap.add_argument("--cutset-hours", type=float, default=1.0, help="hours of audio per rank in the CutSet-level job of `extra`")
+    ap.add_argument("--cutset-hours", type=float, default=4.0, help="hours of audio per rank in the CutSet-level job of `extra`")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -154,11 +154,11 @@ struct Fast2048Tables {
   // one 16-byte-aligned blob (TMA bulk copy):
   //   [win2: 16*2*32 float2 (w[128 n1 + 64 c + 2 lane], w[.. + 1]) indexed [n1][c][lane], zero beyond L]
   //   [tw1: 16*16 float2 W256^(n2*k1) at [k1][n2]] [tw2: 4*256 float2 W1024^(n3*k) at [n3][k]] [w2k: 128 float2 W2048^k]
-  //   [rstart: rounds*32 int | fdesc: M int2 {first item, items} | wdense: rounds*3*32 float4, [round][trip][lane][4]]
+  //   [rstart: rounds*32 int | fdesc: M int2 {first item, items} + ceil(M/32) int2 {max items of the 32 filters, 0} | wdense: rounds*3*32 float4, [round][trip][lane][4]]
   const void *cblob;
   int cblob_bytes;
   int off_tw1, off_tw2, off_w2k, off_rstart, off_fdesc, off_mw;
-  int mel_rounds, mel_qmax;  // rounds (even) of 32 work items; the widest filter's item count
+  int mel_rounds, mel_qmax;  // rounds (even) of 32 work items; the widest filter's item count (informational)
 };
 
 static inline size_t fast2048_smem_bytes(const Fast2048Tables &t, int warps, int slots) {
@@ -422,8 +422,9 @@ b200feat_fast2048_kernel(const DevPlan p, const Fast2048Tables ft, const DevBatc
         float r[SLOTS];
 #pragma unroll
         for (int f = 0; f < SLOTS; ++f) r[f] = 0.f;
-#pragma unroll 4
-        for (int q = 0; q < ft.mel_qmax; ++q) {  // uniform bound (the widest filter's item count); + 0.f leaves the sum as it is
+        const int qn = s_fdesc[p.M + (m >> 5)].x;  // uniform bound: the item count of the widest filter among these 32; + 0.f leaves a sum as it is
+#pragma unroll 2
+        for (int q = 0; q < qn; ++q) {
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) r[f] += q < fd.y ? part[f * NQ + fd.x + q] : 0.f;
         }
@@ -574,8 +575,12 @@ static inline int fast2048_prepare(DevPlan &p, const std::vector<float> &bank, s
     hst.t.off_tw2 = append(tw2.data(), tw2.size() * sizeof(float2));
     hst.t.off_w2k = append(w2k.data(), w2k.size() * sizeof(float2));
     hst.t.off_rstart = append(mr.rstart.data(), mr.rstart.size() * sizeof(int));
-    std::vector<int> fdesc((size_t)std::max(p.M, 1) * 2, 0);
-    for (int m = 0; m < p.M; ++m) { fdesc[2 * m] = mr.qfirst[m]; fdesc[2 * m + 1] = mr.qcount[m]; }
+    std::vector<int> fdesc((size_t)(std::max(p.M, 1) + (p.M + 31) / 32 + 1) * 2, 0);  // M x {first item, items}, then per 32 filters {max items, 0}
+    for (int m = 0; m < p.M; ++m) {
+      fdesc[2 * m] = mr.qfirst[m]; fdesc[2 * m + 1] = mr.qcount[m];
+      int &mx = fdesc[2 * (p.M + m / 32)];
+      mx = std::max(mx, mr.qcount[m]);
+    }
     hst.t.off_fdesc = append(fdesc.data(), fdesc.size() * sizeof(int));
     hst.t.off_mw = append(mr.wdense.data(), mr.wdense.size() * sizeof(float));
     const unsigned char *d = nullptr;
