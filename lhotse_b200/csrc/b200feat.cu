@@ -22,7 +22,6 @@
 #include "fast256.cuh"
 #include "fast1024.cuh"
 #include "fast2048.cuh"
-#include "fast512w.cuh"
 #include "fast400.cuh"
 
 namespace {
@@ -147,8 +146,6 @@ struct b200feat_handle {
   Fast256Host fast256;
   Fast1024Host fast1024;
   Fast2048Host fast2048;
-  Fast512wHost fast512w;
-  bool use_512w = false;  // the warp-per-frame N = 512 kernel (fast512w.cuh) instead of fast512.cuh
   Fast400Host fast400;
 };
 
@@ -407,15 +404,7 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
     else if (h->plan.N == 400) rc = fast400_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast400);
     else if (h->plan.N == 1024) rc = fast1024_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast1024);
     else if (h->plan.N == 2048) rc = fast2048_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast2048);
-    else {
-      const char *fv = getenv("B200FEAT_FAST_VARIANT");
-      h->use_512w = fv && atoi(fv) == 3 && fast512w_supported(h->plan);
-      if (h->use_512w) {
-        rc = fast512w_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast512w);
-        if (rc == B200FEAT_EUNSUPPORTED) { h->use_512w = false; h->frames_per_tile = 1; }
-      }
-      if (!h->use_512w) rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
-    }
+    else rc = fast512_prepare(h->plan, h->h_bank, h->allocs, &h->frames_per_tile, h->h_window, &h->fast);
     if (rc == B200FEAT_EUNSUPPORTED && desc->kernel == B200FEAT_KERNEL_AUTO) {
       h->kernel = B200FEAT_KERNEL_GENERIC;  // e.g. the plan's tables do not fit the fast kernel's shared memory
       h->frames_per_tile = 1;
@@ -581,9 +570,6 @@ static int launch_range(b200feat_handle *h, const void *samples_dev, int32_t dt,
   } else if (h->kernel == B200FEAT_KERNEL_FAST && h->plan.N == 2048) {
     int rc = fast2048_launch(h->plan, h->fast2048, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast2048 launch: ") + cudaGetErrorString((cudaError_t)rc));
-  } else if (h->kernel == B200FEAT_KERNEL_FAST && h->use_512w) {
-    int rc = fast512w_launch(h->plan, h->fast512w, db, dt, h->sm_count, stream);
-    if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512w launch: ") + cudaGetErrorString((cudaError_t)rc));
   } else if (h->kernel == B200FEAT_KERNEL_FAST) {
     int rc = fast512_launch(h->plan, h->fast, db, dt, h->sm_count, stream);
     if (rc) return fail(h, B200FEAT_ECUDA, std::string("fast512 launch: ") + cudaGetErrorString((cudaError_t)rc));
