@@ -89,6 +89,9 @@ class B200FbankConfig(_ConfigMixin):
     kernel: str = "auto"  # auto | fast | tc | generic
     compat: str = "lhotse"  # "torchaudio": Kaldi log-energy convention + 2*pi/(L-1) blackman (TorchaudioFbank / KaldifeatFbank)
     blackman_coeff: float = 0.42  # window_type="blackman" only (kaldifeat frame_opts.blackman_coeff, kaldifeat.py:24)
+    vtln_low: float = 100.0   # vtln_* : the torchaudio family's VTLN warp of the mel filter edges (fbank.py:30-32); 1.0 = off
+    vtln_high: float = -500.0
+    vtln_warp: float = 1.0
 
 
 @dataclass
@@ -120,6 +123,9 @@ class B200MfccConfig(_ConfigMixin):
     kernel: str = "auto"
     compat: str = "lhotse"  # "torchaudio": Kaldi log-energy convention, C0 <- energy (TorchaudioMfcc / KaldifeatMfcc)
     blackman_coeff: float = 0.42  # window_type="blackman" only
+    vtln_low: float = 100.0   # vtln_* : the torchaudio family's VTLN warp of the mel filter edges (fbank.py:30-32); 1.0 = off
+    vtln_high: float = -500.0
+    vtln_warp: float = 1.0
 
 
 @dataclass
@@ -672,9 +678,9 @@ def from_reference_config(cfg: Any, device: str = "cuda", sampling_rate: int = 1
                  round_to_power_of_two=cfg.round_to_power_of_two, remove_dc_offset=cfg.remove_dc_offset,
                  preemph_coeff=cfg.preemphasis_coefficient, window_type=cfg.window_type, dither=cfg.dither,
                  energy_floor=cfg.energy_floor, raw_energy=cfg.raw_energy, use_energy=cfg.use_energy,
-                 low_freq=cfg.low_freq, high_freq=cfg.high_freq, num_filters=cfg.num_mel_bins)
-        if getattr(cfg, "vtln_warp", 1.0) != 1.0:
-            raise ValueError("vtln_warp != 1.0 is not supported")
+                 low_freq=cfg.low_freq, high_freq=cfg.high_freq, num_filters=cfg.num_mel_bins,
+                 vtln_low=getattr(cfg, "vtln_low", 100.0), vtln_high=getattr(cfg, "vtln_high", -500.0),
+                 vtln_warp=getattr(cfg, "vtln_warp", 1.0))
     elif hasattr(cfg, "frame_opts"):  # kaldifeat family
         fo, mo = cfg.frame_opts, cfg.mel_opts
         if getattr(cfg, "htk_compat", False) or not getattr(cfg, "use_log_fbank", True):

@@ -22,7 +22,8 @@ Family-specific behaviour kept from the reference:
     (base.py:421-424); `snip_edges` is always False (base.py:414).
   * kaldifeat's `extract` takes a single waveform OR a list / 2-D batch of waveforms and `extract_batch(..., lengths)`
     trims and forwards to it (kaldifeat.py:78-141); numpy in -> numpy out, tensors in -> tensors on the device.
-Not supported (raise ValueError at construction / first use): `vtln_warp != 1`, `min_duration != 0`, `htk_compat=True`,
+`vtln_warp != 1` (torchaudio family) warps the mel filter edges exactly as torchaudio's `get_mel_banks` does (plan.py, bit-equal tables).
+Not supported (raise ValueError at construction / first use): `min_duration != 0`, `htk_compat=True`,
 `use_log_fbank=False`, `htk_mode=True`.
 kaldifeat itself is an un-vendored, unpinned optional dependency (setup.py:188) that cannot be installed here: its parity
 is anchored, as in the reference's own test (test/features/test_kaldifeat_features.py:103-116), on agreement with `Fbank` /
@@ -277,7 +278,7 @@ class _TorchaudioFamily(_FamilyExtractor):
     def _validate(self):
         if self.config.min_duration != 0.0:
             raise ValueError("min_duration != 0 is not supported")
-        self._inner(16000).plan  # builds the tables once: raises on vtln_warp != 1, bad window names, ...
+        self._inner(16000).plan  # builds the tables once: raises on bad VTLN cut-offs, bad window names, ...
         self._inner_by_sr = {}
 
     @property

@@ -55,6 +55,58 @@ def _lin2mel(x):
     return 1127.0 * np.log(1 + x / 700)
 
 
+def _make_mel_bank_vtln(M, N, sr, low_freq, high_freq, vtln_low, vtln_high, warp) -> np.ndarray:
+    """The Kaldi mel bank with VTLN warping, in float32 torch arithmetic ordered as torchaudio orders it (all-tensor mel scale,
+    `1127 * log(1 + f / 700)` and its inverse) so that the weights come out bit-equal.  The warp F is continuous and piecewise
+    linear on [low, high] with F(low) = low, F(high) = high and F(f) = f / warp between the knees
+    l = vtln_low * max(1, warp) and h = vtln_high * min(1, warp)."""
+    if M <= 3:
+        raise ValueError("Must have at least 3 mel bins")
+    if N % 2 != 0:
+        raise ValueError("the Kaldi mel scale needs an even fft length")
+    nyquist = 0.5 * sr
+    hi = high_freq + nyquist if high_freq <= 0.0 else high_freq
+    if not (0.0 <= low_freq < nyquist and 0.0 < hi <= nyquist and low_freq < hi):
+        raise ValueError(f"Bad values in options: low-freq {low_freq} and high-freq {hi} vs. nyquist {nyquist}")
+    vhi = vtln_high + nyquist if vtln_high < 0.0 else vtln_high
+    if not (low_freq < vtln_low < hi and 0.0 < vhi < hi and vtln_low < vhi):
+        raise ValueError(f"Bad values in options: vtln-low {vtln_low} and vtln-high {vhi}, versus low-freq {low_freq} and high-freq {hi}")
+    knee_lo = vtln_low * max(1.0, warp)
+    knee_hi = vhi * min(1.0, warp)
+    if not (knee_lo > low_freq and knee_hi < hi):
+        raise ValueError(f"vtln_warp {warp} moves the warp's knees outside ({low_freq}, {hi})")
+    scale = 1.0 / warp
+    slope_lo = (scale * knee_lo - low_freq) / (knee_lo - low_freq)
+    slope_hi = (hi - scale * knee_hi) / (hi - knee_hi)
+
+    def to_mel(f):
+        return 1127.0 * (1.0 + f / 700.0).log()
+
+    def warped(mel_edges):
+        f = 700.0 * ((mel_edges / 1127.0).exp() - 1.0)
+        out = hi + slope_hi * (f - hi)                                  # above the upper knee
+        out = torch.where(f < knee_hi, scale * f, out)                   # between the knees
+        out = torch.where(f < knee_lo, low_freq + slope_lo * (f - low_freq), out)
+        out = torch.where((f < low_freq) | (f > hi), f, out)             # outside [low, high]: identity
+        return to_mel(out)
+
+    mel_lo = 1127.0 * math.log(1.0 + low_freq / 700.0)
+    mel_hi = 1127.0 * math.log(1.0 + hi / 700.0)
+    delta = (mel_hi - mel_lo) / (M + 1)
+    b = torch.arange(M).unsqueeze(1)
+    left, center, right = warped(mel_lo + b * delta), warped(mel_lo + (b + 1.0) * delta), warped(mel_lo + (b + 2.0) * delta)
+    mel = to_mel((sr / N) * torch.arange(N / 2)).unsqueeze(0)
+    up = (mel - left) / (center - left)
+    down = (right - mel) / (right - center)
+    bank = torch.zeros_like(up)
+    rising = (mel > left) & (mel <= center)
+    falling = (mel > center) & (mel < right)
+    bank = torch.where(rising, up, bank)
+    bank = torch.where(falling, down, bank)
+    bank = torch.nn.functional.pad(bank, (0, 1), mode="constant", value=0).T
+    return np.ascontiguousarray(bank.to(torch.float32).numpy())
+
+
 def make_mel_bank(
     num_filters: int,
     fft_length: int,
@@ -63,9 +115,16 @@ def make_mel_bank(
     high_freq: float,
     torchaudio_compatible: bool = True,
     norm_filters: bool = False,
+    vtln_low: float = 100.0,
+    vtln_high: float = -500.0,
+    vtln_warp: float = 1.0,
 ) -> np.ndarray:
-    """Dense (K = N//2 + 1, M) float32 bank, equal to the reference's ``_fb``."""
+    """Dense (K = N//2 + 1, M) float32 bank, equal to the reference's ``_fb``.  `vtln_warp != 1` (the torchaudio family only:
+    `TorchaudioFbankConfig.vtln_*`, lhotse/features/fbank.py:30-32, handed to `torchaudio.compliance.kaldi.fbank`) moves the
+    filter edges through Kaldi's piecewise-linear VTLN warp; the table is then bit-equal to torchaudio's `get_mel_banks`."""
     M, N, sr = num_filters, fft_length, sampling_rate
+    if torchaudio_compatible and vtln_warp != 1.0:
+        return _make_mel_bank_vtln(M, N, sr, low_freq, high_freq, vtln_low, vtln_high, vtln_warp)
     if torchaudio_compatible:
         if M <= 3:
             raise ValueError("Must have at least 3 mel bins")  # layers.py:976
@@ -277,8 +336,6 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
     if dither < 0.0:
         raise ValueError("dither must be >= 0")
     vtln = float(_get(melo, "vtln_warp", default=1.0))
-    if vtln != 1.0:
-        raise ValueError("vtln_warp != 1.0 is not supported")
     if bool(_get(cfg, "htk_compat", default=False)):
         raise ValueError("htk_compat=True is not supported")
     if not bool(_get(cfg, "use_log_fbank", default=True)):
@@ -318,6 +375,9 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
             float(_get(melo, "high_freq", default=-400.0)),
             torchaudio_compatible=bool(_get(cfg, "torchaudio_compatible_mel_scale", default=True)),
             norm_filters=bool(_get(cfg, "norm_filters", default=False)),
+            vtln_low=float(_get(melo, "vtln_low", default=100.0)),
+            vtln_high=float(_get(melo, "vtln_high", default=-500.0)),
+            vtln_warp=vtln,
         )
     if feature == "mfcc":
         C = int(_get(cfg, "num_ceps", default=13))

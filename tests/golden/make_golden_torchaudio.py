@@ -28,6 +28,10 @@ CASES = [
     ("mfcc", {}),
     ("mfcc", dict(use_energy=True)),
     ("mfcc", dict(num_ceps=20, num_mel_bins=40, cepstral_lifter=0.0)),
+    # VTLN warping of the filter edges (appended in round 2: the earlier cases keep their random draws)
+    ("fbank", dict(vtln_warp=1.1)),
+    ("fbank", dict(vtln_warp=0.9, num_mel_bins=40, use_energy=True)),
+    ("mfcc", dict(vtln_warp=1.15, vtln_low=200.0, vtln_high=-800.0)),
 ]
 
 

@@ -110,13 +110,36 @@ def test_family_registry_names_and_round_trips(tmp_path):
         again = FeatureExtractor.from_yaml(path)
         assert type(again).__name__ == cls.__name__ and again.config.to_dict() == ext.config.to_dict()
         assert pickle.loads(pickle.dumps(ext)).config.to_dict() == ext.config.to_dict()
-    for bad in (dict(vtln_warp=1.2), dict(min_duration=0.5), dict(window_type="kaiser")):
+    for bad in (dict(vtln_warp=1.2, vtln_low=10.0), dict(min_duration=0.5), dict(window_type="kaiser")):  # vtln_low below low_freq
         with pytest.raises(ValueError):
             fam.B200TorchaudioFbank(fam.B200TorchaudioFbankConfig(**bad))
     with pytest.raises(ValueError):
         fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(htk_compat=True))
     with pytest.raises(ValueError):
         fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(use_log_fbank=False))
+
+
+def test_vtln_mel_bank_bit_equal_to_torchaudio():
+    """`vtln_warp != 1` (TorchaudioFbankConfig.vtln_*, lhotse/features/fbank.py:30-32 -> torchaudio.compliance.kaldi.fbank): the
+    warped filter bank is the table torchaudio builds, bit for bit, and the plan carries it."""
+    K = pytest.importorskip("torchaudio.compliance.kaldi")
+    import lhotse_b200.families as fam
+    from lhotse_b200.plan import build_plan, make_mel_bank
+
+    for M, N, sr, lo, hi, vlo, vhi, warp in ((80, 512, 16000, 20.0, -400.0, 100.0, -500.0, 1.1), (40, 512, 16000, 20.0, -400.0, 100.0, -500.0, 0.9),
+                                             (23, 256, 8000, 20.0, 3700.0, 200.0, -800.0, 1.15), (80, 1024, 24000, 0.0, 0.0, 60.0, 11000.0, 0.8),
+                                             (128, 2048, 44100, 20.0, -400.0, 100.0, -500.0, 1.25)):
+        want, _ = K.get_mel_banks(M, N, float(sr), lo, hi, vlo, vhi, warp)
+        want = torch.nn.functional.pad(want, (0, 1)).T.numpy()
+        got = make_mel_bank(M, N, sr, lo, hi, vtln_low=vlo, vtln_high=vhi, vtln_warp=warp)
+        assert got.dtype == np.float32 and got.shape == want.shape == (N // 2 + 1, M)
+        assert np.array_equal(got, want), (M, N, warp, float(np.abs(got - want).max()))
+        assert not np.array_equal(got, make_mel_bank(M, N, sr, lo, hi))  # the warp does move the filters
+    plan = build_plan("fbank", fam.B200TorchaudioFbankConfig(vtln_warp=1.1))
+    want, _ = K.get_mel_banks(80, 512, 16000.0, 20.0, -400.0, 100.0, -500.0, 1.1)
+    assert np.array_equal(np.asarray(plan.mel_bank), torch.nn.functional.pad(want, (0, 1)).T.numpy())
+    inner = fam.B200TorchaudioMfcc(fam.B200TorchaudioMfccConfig(vtln_warp=1.15, vtln_low=200.0, vtln_high=-800.0, device="cpu"))._inner(16000)
+    assert (inner.config.vtln_warp, inner.config.vtln_low, inner.config.vtln_high) == (1.15, 200.0, -800.0)
 
 
 def test_family_container_rules_on_the_oracle_engine():
