@@ -20,8 +20,8 @@
 #include "fast512.cuh"
 #include "tc512.cuh"
 #include "fast256.cuh"
-#include "fast1024.cuh"
 #include "fast2048.cuh"
+#include "fast1024.cuh"
 #include "fast400.cuh"
 
 namespace {

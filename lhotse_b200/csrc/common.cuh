@@ -146,7 +146,10 @@ struct MelRounds {
   int max_reach = 0;          // max over lanes of (first bin + trip count): how far zero-weight over-reads go
 };
 
-static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, int M, float scale, int lanes = 16, int align = 1) {
+static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, int M, float scale, int lanes = 16, int align = 1,
+                                        int limit = 0) {
+  // limit > 0: no lane may read past bin `limit` (the P row's padded length): a short filter at the top of the band that shares
+  // its round with a wide one starts earlier instead, with zero weights in front (e.g. a 40-filter bank warped by VTLN 0.9)
   // align > 1: every filter starts on a multiple of `align` bins and trip counts are multiples of `align` (zero weights
   // fill the gaps), and the weights of `align` consecutive taps of one lane are adjacent: [row / align][lane][align],
   // so the epilogue can use 64/128-bit shared-memory loads for both operands.
@@ -169,6 +172,14 @@ static inline MelRounds pack_mel_rounds(const std::vector<float> &bank, int K, i
       r.rstart[j * lanes + l] = first[l];
     }
     mx = (mx + align - 1) / align * align;
+    if (limit > 0 && mx <= limit)
+      for (int l = 0; l < lanes; ++l)
+        if (len[l] > 0 && first[l] + mx > limit) {
+          const int nf = (limit - mx) / align * align;
+          len[l] += first[l] - nf;
+          first[l] = nf;
+          r.rstart[j * lanes + l] = nf;
+        }
     for (int l = 0; l < lanes; ++l) r.max_reach = std::max(r.max_reach, first[l] + mx);
     r.rlen[j] = mx;
     r.rrow[j] = (int)(r.wdense.size() / lanes);

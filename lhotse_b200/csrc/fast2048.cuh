@@ -13,7 +13,7 @@
 //            real-FFT split needs no shuffle and no further exchange:  E = Z[kappa] + conj Z[1024-kappa], O = Z[kappa] - conj(..),
 //            T = W2048^kappa * O, 2 X[kappa] = E - iT, 2 conj X[1024-kappa] = E + iT; W2048^kappa = W2048^k * W8^k3 (table x
 //            immediates).  Lane 0 also owns the two self-mirrored residues k = 0 and k = 128.
-//   power spectra of SLOTS consecutive frames staged as P[slot][bin] (1025 bins), mel rounds of 32 filters as in fast1024.cuh.
+//   power spectra of SLOTS consecutive frames staged as P[slot][bin] (1025 bins), mel bank as balanced 12-tap work items (below).
 //
 // Loads are coalesced 8-byte pairs (y[128*n1 + 2*lane], y[.. + 64]); the pre-emphasis neighbour comes from the adjacent lane
 // by shuffle.  The stage functions are __host__ __device__: scripts/micro/f2k_host_check.cu runs them lane by lane on the CPU
@@ -22,7 +22,7 @@
 // Replaces the same reference code as fast512.cuh (lhotse/features/kaldi/layers.py:151-186, :32-42, :565-578, :708-724,
 // framing :727-772).
 #pragma once
-#include "fast1024.cuh"
+#include "fast512.cuh"
 
 #define F2K_PBINS 1040                     // floats per P row: 1025 bins + zero pad (a mel piece starting at bin 1024 reads 12 taps)
 #define F2K_PTAIL 64
@@ -87,12 +87,12 @@ F512_HD void f2k_stage2_store(int lane, float2 (&u0)[16], float2 (&u1)[16], cons
   }
 }
 
-// one (Z[kappa], Z[1024 - kappa]) pair -> |2 X[kappa]|^2 and |2 X[1024 - kappa]|^2 (or the moduli); wk = W2048^(kappa - 256*k3)
+// one (Z[kappa], Z[4Q - kappa]) pair -> |2 X[kappa]|^2 and |2 X[4Q - kappa]|^2 (or the moduli); wk = exp(-2 pi i (kappa - Q*k3) / (8Q))
 F512_HD void f2k_pair(float2 zk, float2 zm, float2 wk, int k3, bool use_mag, float &pa, float &pb) {
   const float2 cc = f2conj(zm);
   const float2 E = f2add(zk, cc), O = f2sub(zk, cc);
   float2 T = f2k_mul(O, wk);
-  if (k3 == 1) T = f2mul_w8_1(T);       // W2048^(256*k3) = W8^k3
+  if (k3 == 1) T = f2mul_w8_1(T);       // exp(-2 pi i Q*k3 / (8Q)) = W8^k3
   else if (k3 == 2) T = f2mi(T);
   else if (k3 == 3) T = f2mul_w8_3(T);
   const float2 mit = f2mi(T);           // -i*T
@@ -102,24 +102,26 @@ F512_HD void f2k_pair(float2 zk, float2 zm, float2 wk, int k3, bool use_mag, flo
   if (use_mag) { pa = sqrtf(pa); pb = sqrtf(pb); }
 }
 
-// ---- stage 3 + real-FFT split + power: w2k[k] = W2048^k, k < 128; Pf[0..1024]
-F512_HD void f2k_stage3(int lane, const float4 *xb, const float2 *w2k, float *Pf, bool use_mag) {
+// ---- stage 3 + real-FFT split + power for a packed complex FFT of 4*Q points (Q = 256: N = 2048; Q = 128: N = 1024, fast1024.cuh):
+// tile B holds Z'[k][n3] as two planes of float4 (n3 = 0,1 | 2,3), k < Q; wk[k] = exp(-2 pi i k / (8 Q)), k < Q / 2; Pf[0 .. 4Q]
+template <int Q, int PLANE>
+F512_HD void f2k_stage3_t(int lane, const float4 *xb, const float2 *wk_table, float *Pf, bool use_mag) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < Q / 64; ++j) {
     const int ka = lane + 32 * j;
-    const int kb = (j == 0 && lane == 0) ? 128 : 256 - ka;
+    const int kb = (j == 0 && lane == 0) ? Q / 2 : Q - ka;
     float2 a[4], q[4];
     {
-      const float4 r0 = xb[ka], r1 = xb[F2K_PLANE + ka];
+      const float4 r0 = xb[ka], r1 = xb[PLANE + ka];
       a[0] = make_float2(r0.x, r0.y); a[1] = make_float2(r0.z, r0.w);
       a[2] = make_float2(r1.x, r1.y); a[3] = make_float2(r1.z, r1.w);
-      dft4(a[0], a[1], a[2], a[3]);  // a[k3] = Z[ka + 256*k3]
-      const float4 s0 = xb[kb], s1 = xb[F2K_PLANE + kb];
+      dft4(a[0], a[1], a[2], a[3]);  // a[k3] = Z[ka + Q*k3]
+      const float4 s0 = xb[kb], s1 = xb[PLANE + kb];
       q[0] = make_float2(s0.x, s0.y); q[1] = make_float2(s0.z, s0.w);
       q[2] = make_float2(s1.x, s1.y); q[3] = make_float2(s1.z, s1.w);
-      dft4(q[0], q[1], q[2], q[3]);  // q[k3] = Z[kb + 256*k3]
+      dft4(q[0], q[1], q[2], q[3]);  // q[k3] = Z[kb + Q*k3]
     }
-    // mirror of kappa = ka + 256*k3 is kb + 256*(3 - k3); lane 0, j = 0 (ka = 0): 1024 - 256*k3 = 256*(4 - k3), with Z[1024] = Z[0]
+    // mirror of kappa = ka + Q*k3 is kb + Q*(3 - k3); lane 0, j = 0 (ka = 0): 4Q - Q*k3 = Q*(4 - k3), with Z[4Q] = Z[0]
     float2 m[4] = {q[3], q[2], q[1], q[0]};
     if (j == 0) {
       const bool z = lane == 0;
@@ -128,26 +130,31 @@ F512_HD void f2k_stage3(int lane, const float4 *xb, const float2 *w2k, float *Pf
       m[2] = z ? a[2] : m[2];
       m[3] = z ? a[1] : m[3];
     }
-    const float2 wk = w2k[ka];
+    const float2 wk = wk_table[ka];
 #pragma unroll
     for (int k3 = 0; k3 < 4; ++k3) {
       float pa, pb;
       f2k_pair(a[k3], m[k3], wk, k3, use_mag, pa, pb);
-      const int kappa = ka + 256 * k3;
+      const int kappa = ka + Q * k3;
       Pf[kappa] = pa;
-      Pf[1024 - kappa] = pb;
+      Pf[4 * Q - kappa] = pb;
     }
-    if (j == 0 && lane == 0) {  // the other self-mirrored residue: kappa = 128 + 256*k3 <-> 128 + 256*(3 - k3)
+    if (j == 0 && lane == 0) {  // the other self-mirrored residue: kappa = Q/2 + Q*k3 <-> Q/2 + Q*(3 - k3)
 #pragma unroll
       for (int k3 = 0; k3 < 2; ++k3) {
         float pa, pb;
-        f2k_pair(q[k3], q[3 - k3], make_float2(F512_C1, -F512_S1), k3, use_mag, pa, pb);  // W2048^128 = W16^1
-        const int kappa = 128 + 256 * k3;
+        f2k_pair(q[k3], q[3 - k3], make_float2(F512_C1, -F512_S1), k3, use_mag, pa, pb);  // exp(-2 pi i (Q/2) / (8Q)) = W16^1
+        const int kappa = Q / 2 + Q * k3;
         Pf[kappa] = pa;
-        Pf[1024 - kappa] = pb;
+        Pf[4 * Q - kappa] = pb;
       }
     }
   }
+}
+
+// w2k[k] = W2048^k, k < 128; Pf[0..1024]
+F512_HD void f2k_stage3(int lane, const float4 *xb, const float2 *w2k, float *Pf, bool use_mag) {
+  f2k_stage3_t<256, F2K_PLANE>(lane, xb, w2k, Pf, use_mag);
 }
 
 struct Fast2048Tables {

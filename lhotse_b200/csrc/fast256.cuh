@@ -411,7 +411,7 @@ static inline int fast256_prepare(DevPlan &p, const std::vector<float> &bank, st
   int rc;
   if ((rc = f512_upload(tw1, allocs, &hst.t.tw1))) return rc;
   if ((rc = f512_upload(w256, allocs, &hst.t.w256))) return rc;
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 8, 2);  // 64-bit mel loads
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 8, 2, F256_PBINS);  // 64-bit mel loads
   if (mr.max_reach > F256_PBINS) return B200FEAT_EUNSUPPORTED;
   hst.t.mel_rounds = mr.rounds;
   hst.t.mel_wrows = mr.rows;

@@ -421,7 +421,7 @@ static inline int fast400_prepare(DevPlan &p, const std::vector<float> &bank, st
       const double a = -2.0 * M_PI * (double)k / 400.0;
       tws[r * 8 + l] = make_float2((float)cos(a), (float)sin(a));
     }
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, 4);  // 16 filters per round, two per lane
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, 4, F400_PBINS / 4 * 4);  // 16 filters per round, two per lane
   if (mr.max_reach > F400_PBINS) return B200FEAT_EUNSUPPORTED;
   hst.t.mel_rounds = mr.rounds;
   int rc;

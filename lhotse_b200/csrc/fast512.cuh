@@ -650,7 +650,7 @@ static inline int fast512_prepare(DevPlan &p, const std::vector<float> &bank, st
   if ((rc = f512_upload(w512, allocs, &hst.t.w512))) return rc;
   // mel bank re-packed for the epilogue (pack_mel_rounds, common.cuh); the kernel stores |2X|^2 (or |2X|), so the
   // exact power-of-two factor 1/4 (1/2) rides on the weights
-  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, 4);  // 4-aligned filter starts: 128-bit mel loads
+  const MelRounds mr = pack_mel_rounds(bank, p.K, p.M, p.use_mag ? 0.5f : 0.25f, 16, 4, 260);  // 4-aligned filter starts: 128-bit mel loads
   if (mr.max_reach > 260) return B200FEAT_EUNSUPPORTED;  // zero-weight over-reads must stay inside the frame's own P row
   const int rounds = mr.rounds;
   const std::vector<int> &rstart = mr.rstart, &rlen = mr.rlen, &rrow = mr.rrow;

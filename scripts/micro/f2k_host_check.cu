@@ -8,7 +8,7 @@
 
 #include <vector>
 
-#include "../../lhotse_b200/csrc/fast2048.cuh"
+#include "../../lhotse_b200/csrc/fast1024.cuh"
 
 int main(int argc, char **argv) {
   const int L = argc > 1 ? atoi(argv[1]) : 2048;
@@ -90,5 +90,46 @@ int main(int argc, char **argv) {
   printf("mel items: piece %d taps, %d items in %d rounds, %d weight rows (whole-filter rounds: %d rows), simulated wavefronts %ld, "
          "reach %d; worst relative error %.3g, %d bad\n", mi.piece, mi.items, mi.rounds, mi.rows, mo.rows, mi.cost, mi.max_reach, mworst, mbad);
 
-  return (bad || mbad) ? 1 : 0;
+  // ---- the N = 1024 stages (fast1024.cuh): 512-point complex FFT as 16 x 8 x 4 + the same in-lane split with Q = 128
+  int wbad = 0;
+  {
+    const int L1 = L > 1024 ? 600 : (L < 3 ? 3 : L);
+    std::vector<float> y1(1024, 0.f);
+    for (int i = 0; i < L1; ++i) y1[i] = (float)rand() / RAND_MAX - 0.5f + (i % 5 == 0 ? 0.25f : 0.f);
+    std::vector<float2> t1, t2, wk;
+    f1w_fft_tables(t1, t2, wk);
+    std::vector<float2> X1(F1W_XBUF, make_float2(NAN, NAN));
+    std::vector<float> P1(F1W_PBINS, NAN);
+    static float2 v1w[32][16], u1w[32][8];
+    for (int lane = 0; lane < 32; ++lane)
+      for (int n1 = 0; n1 < 16; ++n1) v1w[lane][n1] = make_float2(y1[64 * n1 + 2 * lane], y1[64 * n1 + 2 * lane + 1]);
+    for (int lane = 0; lane < 32; ++lane) f1w_stage1(lane, v1w[lane], t1.data(), X1.data());
+    for (int lane = 0; lane < 32; ++lane) f1w_stage2_load(lane, X1.data(), v1w[lane], u1w[lane]);
+    for (auto &x : X1) x = make_float2(NAN, NAN);
+    for (int lane = 0; lane < 32; ++lane) {
+      float2 tw[16];
+      for (int i = 0; i < 16; ++i) tw[i] = t2[lane * 16 + i];
+      f1w_stage2_store(lane, v1w[lane], u1w[lane], tw, reinterpret_cast<float4 *>(X1.data()));
+    }
+    for (int lane = 0; lane < 32; ++lane)
+      f2k_stage3_t<128, F1W_PLANE>(lane, reinterpret_cast<const float4 *>(X1.data()), wk.data(), P1.data(), false);
+    double w1 = 0.0, sc = 0.0;
+    std::vector<double> r1(513);
+    for (int k = 0; k <= 512; ++k) {
+      double re = 0.0, im = 0.0;
+      for (int n = 0; n < 1024; ++n) {
+        const double a = -2.0 * M_PI * (double)((n * k) % 1024) / 1024.0;
+        re += y1[n] * cos(a); im += y1[n] * sin(a);
+      }
+      r1[k] = 4.0 * (re * re + im * im);
+      sc = fmax(sc, r1[k]);
+    }
+    for (int k = 0; k <= 512; ++k) {
+      const double err = fabs((double)P1[k] - r1[k]) / (r1[k] + 1e-3 * sc);
+      if (!(err < 2e-5)) { if (wbad < 10) printf("1024w bin %d: got %.9g want %.9g\n", k, P1[k], r1[k]); ++wbad; }
+      w1 = fmax(w1, err);
+    }
+    printf("fast1024 stages L=%d: worst relative error %.3g over 513 bins, %d bad\n", L1, w1, wbad);
+  }
+  return (bad || mbad || wbad) ? 1 : 0;
 }
