@@ -29,7 +29,11 @@ PLANS = [
     ("fast1024 librosa", lb.B200LibrosaFbank(), 22050),
     ("generic fbank", lb.B200Fbank(lb.B200FbankConfig(kernel="generic")), 16000),
     ("generic whisper", lb.B200WhisperFbank(lb.B200WhisperFbankConfig(kernel="generic")), 16000),
-    ("generic N=2048", lb.B200Fbank(lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05)), 24000),
+    ("fast2048 fbank 24k/50ms", lb.B200Fbank(lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05)), 24000),
+    ("fast2048 mfcc+energy 44.1k", lb.B200Mfcc(lb.B200MfccConfig(sampling_rate=44100, use_energy=True)), 44100),
+    ("fast2048 spectrogram 48k", lb.B200Spectrogram(lb.B200SpectrogramConfig(sampling_rate=48000)), 48000),
+    ("fast1024 mfcc 22.05k", lb.B200Mfcc(lb.B200MfccConfig(sampling_rate=22050)), 22050),
+    ("generic N=2048", lb.B200Fbank(lb.B200FbankConfig(sampling_rate=24000, frame_length=0.05, kernel="generic")), 24000),
     ("generic N=551 (19x29)", lb.B200Spectrogram(lb.B200SpectrogramConfig(sampling_rate=22050, round_to_power_of_two=False)), 22050),
 ]
 total = 0.0
