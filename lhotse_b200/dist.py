@@ -28,11 +28,20 @@ def env_rank_world() -> Tuple[int, int, int]:
 
 
 def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
-    """Initialises torch.distributed from the torchrun environment (no-op for world size 1)."""
+    """Initialises torch.distributed from the torchrun environment (no-op for world size 1).  Returns (rank, world, device index).
+
+    More local ranks than GPUs is allowed for the host-bound jobs (the CutSet-level store spends > 95 % of its wall clock in
+    per-cut Python — manifests, sampler — so several processes per GPU multiply its throughput): local rank r then uses GPU
+    r mod #GPUs, and the job-level collectives (table broadcast, barriers, timing reductions) run over gloo, because NCCL
+    refuses two ranks on one device.  `bench.py` itself always runs one rank per GPU."""
     rank, world, local = env_rank_world()
+    ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    oversubscribed = ngpu > 0 and int(os.environ.get("LOCAL_WORLD_SIZE", world)) > ngpu
+    if ngpu > 0:
+        local = local % ngpu
     if world > 1 and not dist.is_initialized():
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            backend = "nccl" if ngpu > 0 and not oversubscribed else "gloo"
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         kw = {}
         if backend == "nccl":

@@ -101,7 +101,7 @@ def run_cutset_job(rank, world, local, seconds_of_audio=3600.0, cut_seconds=10.0
     mine_s = time.perf_counter() - t0
     lbd.barrier()
     wall = lbd.all_reduce_stats([time.perf_counter() - t0], "max")[0]
-    res = {"unit": "h_audio/s", "n_gpus": world, "cuts": nper * world, "cut_seconds": cut_seconds, "hours_of_audio": nper * world * cut_seconds / 3600.0,
+    res = {"unit": "h_audio/s", "n_gpus": min(world, torch.cuda.device_count()), "ranks": world, "cuts": nper * world, "cut_seconds": cut_seconds, "hours_of_audio": nper * world * cut_seconds / 3600.0,
            "wall_s": wall, "value": nper * world * cut_seconds / 3600.0 / wall, "rank0_s": mine_s, "num_workers": num_workers,
            "batch_duration_s": batch_duration, "kernel": ext.engine.kernel, "storage": "b200_archive on " + base,
            "note": "lazy CutSet -> rank::world shard -> compute_and_store_features_sharded(fused=True): PCM16 file reads into a pinned ring, H2D, "
