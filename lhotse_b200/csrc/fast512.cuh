@@ -253,6 +253,8 @@ b200feat_fast512_kernel(const DevPlan p, const Fast512Tables ft, const DevBatch 
   for (int64_t tg = blockIdx.x; tg < b.num_tiles; tg += gridDim.x) {
     const int64_t tile = b.tile_base + tg;
     const int cut = __ldg(b.tile_cut + tile) - b.batch_first;  // host-built tile->cut table: one load, no search
+    // (fetching the next tile's cut one tile ahead and prefetching its four table rows into L1 before the mel stage was measured
+    // in round 2: 3518 vs 3544 h/s — the two-load chain of this prologue is already hidden by the other warps)
     const int64_t t0 = (tile - __ldg(b.tile_off + cut)) * TILE + (int64_t)hw * SLOTS;
     const int64_t T = __ldg(b.row_off + cut + 1) - __ldg(b.row_off + cut);
     const int64_t rows_here = b.out_mode == B200FEAT_OUT_PADDED ? b.max_frames : T;
