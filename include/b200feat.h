@@ -97,7 +97,8 @@ typedef struct b200feat_plan_desc {
   int32_t num_ceps;     /* C (MFCC only) */
   int32_t snip_edges;   /* layers.py:747-751 */
   int32_t remove_dc_offset;
-  int32_t use_energy;   /* fbank: prepend; spectrograms: overwrite bin 0; mfcc: C0 */
+  int32_t use_energy;   /* 0 off; 1: fbank prepends the log-energy, spectrograms overwrite bin 0, mfcc replaces C0 (first column);
+                           2 (fbank / mfcc): the same value in the LAST column (Kaldi's htk_compat layout) */
   int32_t raw_energy;   /* energy before (1) or after (0) pre-emphasis+window */
   int32_t use_fft_mag;  /* |X| instead of |X|^2 */
   int32_t energy_style; /* B200FEAT_ENERGY_* */

@@ -275,7 +275,8 @@ int b200feat_create(const b200feat_plan_desc *desc, const float *window, const f
   p.log10_mel = (whisper || log10fb) ? 1 : 0;
   p.pad_left = desc->pad_mode == B200FEAT_PAD_CENTER ? N / 2 : (L - S) / 2;
   p.snip_edges = desc->snip_edges; p.remove_dc = desc->remove_dc_offset;
-  p.use_energy = desc->use_energy; p.raw_energy = desc->raw_energy; p.use_mag = desc->use_fft_mag;
+  p.use_energy = desc->use_energy != 0; p.raw_energy = desc->raw_energy; p.use_mag = desc->use_fft_mag;
+  p.energy_last = desc->use_energy == 2 && (desc->feature == B200FEAT_FBANK || desc->feature == B200FEAT_MFCC);
   p.energy_style = desc->energy_style; p.use_lifter = desc->use_lifter;
   p.preemph = desc->preemph_coeff;
   const bool has_floor = desc->energy_style == B200FEAT_ENERGY_KALDI ? desc->energy_floor != 0.f

@@ -20,6 +20,7 @@ struct DevPlan {
   int whisper;                       // feature == B200FEAT_WHISPER_FBANK: per-cut max + normalise pass, n / S valid frames
   int log10_mel;                     // mel epilogue in log10 (whisper-fbank, librosa-fbank) instead of ln
   int snip_edges, remove_dc, use_energy, raw_energy, use_mag, energy_style, use_lifter;
+  int energy_last;                   // use_energy == 2 (htk_compat): the energy column is the LAST one (fbank: after the mel bins; mfcc: C0's place moved last)
   int nstages;
   int radix[B200_MAX_STAGES];
   float preemph, energy_floor_log, has_energy_floor, mel_floor, log_spec_eps;
@@ -70,6 +71,11 @@ __device__ __forceinline__ float ld_sample(const void *base, int64_t i) {
 __device__ __forceinline__ float post_affine(const DevPlan &p, int col, float v) {
   return p.post_scale ? fmaf(v, __ldg(p.post_scale + col), __ldg(p.post_shift + col)) : v;
 }
+
+// column of the log-energy in an fbank / mfcc row: first (Kaldi default) or last (htk_compat)
+__device__ __forceinline__ int energy_col(const DevPlan &p) { return p.energy_last ? p.F - 1 : 0; }
+// first column of the mel bins in an fbank row
+__device__ __forceinline__ int mel_shift(const DevPlan &p) { return (p.feature == B200FEAT_FBANK && p.use_energy && !p.energy_last) ? 1 : 0; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

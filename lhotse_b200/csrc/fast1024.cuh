@@ -291,7 +291,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         }
       }
     } else {
-      const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      const int shift = mel_shift(p), ecol = energy_col(p);
       const float lgk = p.log10_mel ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (librosa_fbank.py:126) or ln
       const int Mpad = (p.M + 3) & ~3;
       // the exchange tile is idle during the epilogue: [SLOTS][NQ] partial sums of the mel work items, then the log-mel rows (MFCC)
@@ -340,11 +340,11 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
         }
       }
       if (p.feature == B200FEAT_FBANK) {
-        if (shift && lane < nvalid) {
+        if (p.use_energy && lane < nvalid) {
           float v0 = 0.f;
 #pragma unroll
           for (int f = 0; f < SLOTS; ++f) v0 = (lane == f) ? le[f] : v0;
-          out[(int64_t)lane * p.F] = post_affine(p, 0, v0);
+          out[(int64_t)lane * p.F + ecol] = post_affine(p, ecol, v0);
         }
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
@@ -353,7 +353,7 @@ b200feat_fast1024_kernel(const DevPlan p, const Fast1024Tables ft, const DevBatc
           float acc = 0.f;
           for (int m = 0; m < p.M; ++m) acc = fmaf(mlog[f * Mpad + m], __ldg(p.dct + m * p.C + c), acc);
           if (p.use_lifter) acc *= __ldg(p.lifter + c);
-          if (p.use_energy && c == 0) {
+          if (p.use_energy && c == ecol) {
 #pragma unroll
             for (int g = 0; g < SLOTS; ++g) acc = (f == g) ? le[g] : acc;
           }

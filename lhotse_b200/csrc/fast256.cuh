@@ -298,7 +298,7 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
         }
       }
     } else {
-      const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      const int shift = mel_shift(p), ecol = energy_col(p);
       const float lgk = p.log10_mel ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (librosa_fbank.py:126) or ln
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(X);  // the transpose tile is idle during the epilogue
@@ -336,11 +336,11 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
         }
       }
       if (p.feature == B200FEAT_FBANK) {
-        if (shift && l < nvalid) {
+        if (p.use_energy && l < nvalid) {
           float v0 = 0.f;
 #pragma unroll
           for (int f = 0; f < F256_SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
-          out[(int64_t)l * p.F] = post_affine(p, 0, v0);
+          out[(int64_t)l * p.F + ecol] = post_affine(p, ecol, v0);
         }
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
@@ -349,7 +349,7 @@ b200feat_fast256_kernel(const DevPlan p, const Fast256Tables ft, const DevBatch 
           float acc = 0.f;
           for (int m = 0; m < p.M; ++m) acc = fmaf(mlog[f * Mpad + m], __ldg(p.dct + m * p.C + c), acc);
           if (p.use_lifter) acc *= __ldg(p.lifter + c);
-          if (p.use_energy && c == 0) {
+          if (p.use_energy && c == ecol) {
 #pragma unroll
             for (int g = 0; g < F256_SLOTS; ++g) acc = (f == g) ? le[g] : acc;
           }

@@ -307,7 +307,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
         }
       }
     } else {
-      const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      const int shift = mel_shift(p), ecol = energy_col(p);
       const int Mpad = (p.M + 3) & ~3;
       float *mlog = reinterpret_cast<float *>(X);  // the exchange tile is idle during the epilogue
       const float lgk = p.log10_mel ? 0.30102999566398119521f : 0.69314718055994530942f;  // log10 (whisper_fbank.py:67) or ln
@@ -357,11 +357,11 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
         for (int o = 16; o > 0; o >>= 1) vmax = nanmax(vmax, __shfl_xor_sync(F512_FULL, vmax, o));
         if ((tid & 31) == 0 && vmax != __int_as_float(0xff800000)) atomic_max_float(b.cut_max + cut, vmax);
       } else if (p.feature == B200FEAT_FBANK) {
-        if (shift && l < nvalid) {
+        if (p.use_energy && l < nvalid) {
           float v0 = 0.f;
 #pragma unroll
           for (int f = 0; f < F400_SLOTS; ++f) v0 = (l == f) ? le[f] : v0;
-          out[(int64_t)l * p.F] = post_affine(p, 0, v0);
+          out[(int64_t)l * p.F + ecol] = post_affine(p, ecol, v0);
         }
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
@@ -370,7 +370,7 @@ b200feat_fast400_kernel(const DevPlan p, const Fast400Tables ft, const DevBatch 
           float acc = 0.f;
           for (int m = 0; m < p.M; ++m) acc = fmaf(mlog[f * Mpad + m], __ldg(p.dct + m * p.C + c), acc);
           if (p.use_lifter) acc *= __ldg(p.lifter + c);
-          if (p.use_energy && c == 0) {
+          if (p.use_energy && c == ecol) {
 #pragma unroll
             for (int g = 0; g < F400_SLOTS; ++g) acc = (f == g) ? le[g] : acc;
           }

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         out[k] = post_affine(p, k, (k == 0 && p.use_energy) ? le : log_spec_value(p, raw[k]));
     } else {
       float *mlog = reinterpret_cast<float *>(dst);  // scratch (FFT buffer not holding the result)
-      const int shift = (p.feature == B200FEAT_FBANK && p.use_energy) ? 1 : 0;
+      const int shift = mel_shift(p), ecol = energy_col(p);
       float vmax = __int_as_float(0xff800000);  // -inf
       for (int m = lane; m < p.M; m += 32) {
         const int st = __ldg(p.mel_start + m), len = __ldg(p.mel_len + m);
@@ -210,14 +210,14 @@ __global__ void __launch_bounds__(256) b200feat_generic_kernel(const DevPlan p, 
         for (int o = 16; o > 0; o >>= 1) vmax = nanmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         if (lane == 0 && t < n / p.S) atomic_max_float(b.cut_max + cut, vmax);
       } else if (p.feature == B200FEAT_FBANK) {
-        if (shift && lane == 0) out[0] = post_affine(p, 0, le);
+        if (p.use_energy && lane == 0) out[ecol] = post_affine(p, ecol, le);
       } else if (p.feature == B200FEAT_MFCC) {
         __syncwarp();
         for (int c = lane; c < p.C; c += 32) {
           float acc = 0.f;
           for (int m = 0; m < p.M; ++m) acc += mlog[m] * __ldg(p.dct + m * p.C + c);
           if (p.use_lifter) acc *= __ldg(p.lifter + c);
-          if (p.use_energy && c == 0) acc = le;
+          if (p.use_energy && c == ecol) acc = le;
           out[c] = post_affine(p, c, acc);
         }
       }

@@ -136,7 +136,8 @@ def plan_desc(plan: FeaturePlan, kernel: str = "auto") -> PlanDesc:
     d.frame_length, d.frame_shift, d.fft_length = plan.L, plan.S, plan.N
     d.num_filters, d.num_ceps = plan.num_filters, plan.num_ceps
     d.snip_edges, d.remove_dc_offset = int(plan.snip_edges), int(plan.remove_dc_offset)
-    d.use_energy, d.raw_energy, d.use_fft_mag = int(plan.use_energy), int(plan.raw_energy), int(plan.use_fft_mag)
+    d.use_energy = (2 if getattr(plan, "energy_last", False) else 1) if plan.use_energy else 0  # 2: energy column last (htk_compat)
+    d.raw_energy, d.use_fft_mag = int(plan.raw_energy), int(plan.use_fft_mag)
     d.energy_style = plan.energy_style
     d.use_lifter = int(plan.lifter is not None)
     d.kernel = KERNELS[kernel]

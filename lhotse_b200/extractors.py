@@ -92,6 +92,7 @@ class B200FbankConfig(_ConfigMixin):
     vtln_low: float = 100.0   # vtln_* : the torchaudio family's VTLN warp of the mel filter edges (fbank.py:30-32); 1.0 = off
     vtln_high: float = -500.0
     vtln_warp: float = 1.0
+    htk_compat: bool = False  # kaldifeat family: energy / C0 column last (and C0 * sqrt(2) without use_energy), kaldifeat.py:158, :227
 
 
 @dataclass
@@ -126,6 +127,7 @@ class B200MfccConfig(_ConfigMixin):
     vtln_low: float = 100.0   # vtln_* : the torchaudio family's VTLN warp of the mel filter edges (fbank.py:30-32); 1.0 = off
     vtln_high: float = -500.0
     vtln_warp: float = 1.0
+    htk_compat: bool = False  # kaldifeat family: energy / C0 column last (and C0 * sqrt(2) without use_energy), kaldifeat.py:158, :227
 
 
 @dataclass
@@ -683,14 +685,15 @@ def from_reference_config(cfg: Any, device: str = "cuda", sampling_rate: int = 1
                  vtln_warp=getattr(cfg, "vtln_warp", 1.0))
     elif hasattr(cfg, "frame_opts"):  # kaldifeat family
         fo, mo = cfg.frame_opts, cfg.mel_opts
-        if getattr(cfg, "htk_compat", False) or not getattr(cfg, "use_log_fbank", True):
-            raise ValueError("htk_compat=True / use_log_fbank=False are not supported")
+        if not getattr(cfg, "use_log_fbank", True):
+            raise ValueError("use_log_fbank=False is not supported")
         d = dict(sampling_rate=fo.sampling_rate, frame_length=fo.frame_length, frame_shift=fo.frame_shift,
                  round_to_power_of_two=fo.round_to_power_of_two, remove_dc_offset=fo.remove_dc_offset,
                  preemph_coeff=fo.preemph_coeff, window_type=fo.window_type, dither=fo.dither, snip_edges=fo.snip_edges,
                  energy_floor=cfg.energy_floor, raw_energy=cfg.raw_energy, use_energy=cfg.use_energy,
                  low_freq=mo.low_freq, high_freq=mo.high_freq, num_filters=mo.num_bins,
-                 use_fft_mag=not getattr(cfg, "use_power", True), blackman_coeff=float(getattr(fo, "blackman_coeff", 0.42)))
+                 use_fft_mag=not getattr(cfg, "use_power", True), blackman_coeff=float(getattr(fo, "blackman_coeff", 0.42)),
+                 htk_compat=bool(getattr(cfg, "htk_compat", False)))
     else:
         raise ValueError(f"unsupported reference config type {kind}")
     if is_mfcc:

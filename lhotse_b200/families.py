@@ -23,8 +23,9 @@ Family-specific behaviour kept from the reference:
   * kaldifeat's `extract` takes a single waveform OR a list / 2-D batch of waveforms and `extract_batch(..., lengths)`
     trims and forwards to it (kaldifeat.py:78-141); numpy in -> numpy out, tensors in -> tensors on the device.
 `vtln_warp != 1` (torchaudio family) warps the mel filter edges exactly as torchaudio's `get_mel_banks` does (plan.py, bit-equal tables).
-Not supported (raise ValueError at construction / first use): `min_duration != 0`, `htk_compat=True`,
-`use_log_fbank=False`, `htk_mode=True`.
+`htk_compat=True` (kaldifeat family) puts the log-energy / C0 column last (and scales C0 by sqrt(2) without `use_energy`), as Kaldi does;
+pinned by tests/golden/golden_kaldi_htk_v1.npz (torchaudio's Kaldi-compatible functions with `htk_compat=True`).
+Not supported (raise ValueError at construction / first use): `min_duration != 0`, `use_log_fbank=False`, `htk_mode=True`.
 kaldifeat itself is an un-vendored, unpinned optional dependency (setup.py:188) that cannot be installed here: its parity
 is anchored, as in the reference's own test (test/features/test_kaldifeat_features.py:103-116), on agreement with `Fbank` /
 `Mfcc`; the torchaudio family is pinned by tests/golden/golden_torchaudio_v1.npz.

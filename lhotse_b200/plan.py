@@ -240,6 +240,7 @@ class FeaturePlan:
     snip_edges: bool = False
     remove_dc_offset: bool = True
     use_energy: bool = False
+    energy_last: bool = False  # htk_compat (kaldifeat family): the energy / C0 column is the last one instead of the first
     raw_energy: bool = True
     use_fft_mag: bool = False
     energy_style: int = ENERGY_LHOTSE
@@ -336,8 +337,9 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
     if dither < 0.0:
         raise ValueError("dither must be >= 0")
     vtln = float(_get(melo, "vtln_warp", default=1.0))
-    if bool(_get(cfg, "htk_compat", default=False)):
-        raise ValueError("htk_compat=True is not supported")
+    htk = bool(_get(cfg, "htk_compat", default=False))
+    if htk and feature not in ("fbank", "mfcc"):
+        raise ValueError("htk_compat=True applies to fbank / mfcc only")
     if not bool(_get(cfg, "use_log_fbank", default=True)):
         raise ValueError("use_log_fbank=False is not supported")
     use_fft_mag = bool(_get(cfg, "use_fft_mag", default=False))
@@ -386,6 +388,21 @@ def build_plan(feature: str, cfg: Any) -> FeaturePlan:
         plan.num_ceps = C
         plan.dct = make_dct(C, plan.num_filters)
         plan.lifter = make_lifter(C, float(_get(cfg, "cepstral_lifter", default=22)))
+        if htk:
+            # Kaldi's htk_compat for cepstra (kaldifeat MfccOptions.htk_compat; torchaudio/compliance/kaldi.py mfcc: the same steps):
+            # C0 — or the log-energy that replaces it — moves to the LAST column, and without use_energy it is multiplied by sqrt(2)
+            # AFTER the lifter (whose first coefficient is 1).  Expressed as a column permutation of the DCT and the lifter tables,
+            # the sqrt(2) riding on the lifter slot so that the arithmetic keeps the reference's order (matmul, then one multiply).
+            perm = list(range(1, C)) + [0]
+            plan.dct = np.ascontiguousarray(plan.dct[:, perm])
+            lf = plan.lifter if plan.lifter is not None else np.ones(C, dtype=np.float32)
+            lf = np.ascontiguousarray(lf[perm]).astype(np.float32)
+            if not plan.use_energy:
+                lf[-1] = np.float32(lf[-1] * np.float32(math.sqrt(2.0)))
+            plan.lifter = lf
+            plan.energy_last = True
+    elif htk:
+        plan.energy_last = plan.use_energy  # fbank: [mel bins..., log-energy] instead of [log-energy, mel bins...]
     return plan
 
 

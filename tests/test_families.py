@@ -113,8 +113,7 @@ def test_family_registry_names_and_round_trips(tmp_path):
     for bad in (dict(vtln_warp=1.2, vtln_low=10.0), dict(min_duration=0.5), dict(window_type="kaiser")):  # vtln_low below low_freq
         with pytest.raises(ValueError):
             fam.B200TorchaudioFbank(fam.B200TorchaudioFbankConfig(**bad))
-    with pytest.raises(ValueError):
-        fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(htk_compat=True))
+    assert fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(htk_compat=True, use_energy=True))._inner(16000).plan.energy_last
     with pytest.raises(ValueError):
         fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(use_log_fbank=False))
 
@@ -188,6 +187,57 @@ def test_gpu_torchaudio_adapters_golden(i, c, x, y):
     assert np.array_equal(ext.extract(torch.from_numpy(x), 16000), got)   # tensor in -> numpy out, same bits
     b = ext.extract_batch([torch.from_numpy(x), torch.from_numpy(x[:5000])], 16000)
     assert b[0].is_cuda and np.array_equal(b[0].cpu().numpy(), got) and b[1].shape[0] == (5000 + 80) // 160
+
+
+def _htk_golden():
+    import json
+
+    g = np.load(os.path.join(HERE, "golden", "golden_kaldi_htk_v1.npz"))
+    man = json.loads(bytes(g["manifest"]).decode())
+    return [(i, c, g[f"x{i}"], g[f"y{i}"]) for i, c in enumerate(man)]
+
+
+HTK_GOLD = _htk_golden()
+
+
+def test_htk_compat_plan_tables():
+    """htk_compat (kaldifeat.py:158, :227) as table permutations: C0's DCT column and lifter slot move last, sqrt(2) rides on the
+    lifter slot without use_energy; fbank only flags the energy column."""
+    _, fam = _lb()
+    base = fam.B200KaldifeatMfcc(fam.B200KaldifeatMfccConfig(device="cpu"))._inner(16000).plan
+    htk = fam.B200KaldifeatMfcc(fam.B200KaldifeatMfccConfig(htk_compat=True, device="cpu"))._inner(16000).plan
+    C = base.num_ceps
+    assert np.array_equal(htk.dct[:, :-1], base.dct[:, 1:]) and np.array_equal(htk.dct[:, -1], base.dct[:, 0])
+    assert np.array_equal(htk.lifter[:-1], base.lifter[1:]) and htk.lifter[-1] == np.float32(np.float32(1.0) * np.float32(np.sqrt(2.0)))
+    assert htk.energy_last and htk.feature_dim == C
+    e = fam.B200KaldifeatMfcc(fam.B200KaldifeatMfccConfig(htk_compat=True, use_energy=True, device="cpu"))._inner(16000).plan
+    assert e.energy_last and e.lifter[-1] == np.float32(1.0)
+    fb = fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(htk_compat=True, device="cpu"))._inner(16000).plan
+    assert not fb.energy_last and fb.feature_dim == 80  # nothing to move without use_energy
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["generic", "fast"])
+@pytest.mark.parametrize("i,c,x,y", HTK_GOLD, ids=[f"{i}-{c['feature']}" for i, c, _, _ in HTK_GOLD])
+def test_gpu_kaldifeat_htk_compat_golden(kernel, i, c, x, y):
+    """Kaldi's htk_compat layout through the kaldifeat adapters against torchaudio's Kaldi-compatible functions
+    (tests/golden/make_golden_kaldi_htk.py): energy / C0 last, C0 * sqrt(2) without use_energy."""
+    _, fam = _lb()
+    k = c["cfg"]
+    mel = fam.B200KaldifeatMelOptions(num_bins=k["num_bins"])
+    if c["feature"] == "mfcc":
+        ext = fam.B200KaldifeatMfcc(fam.B200KaldifeatMfccConfig(mel_opts=mel, num_ceps=k["num_ceps"], cepstral_lifter=k["cepstral_lifter"],
+                                                                use_energy=k["use_energy"], htk_compat=True, kernel=kernel))
+    else:
+        ext = fam.B200KaldifeatFbank(fam.B200KaldifeatFbankConfig(mel_opts=mel, use_energy=k["use_energy"], htk_compat=True, kernel=kernel))
+    got = ext.extract(x, 16000)
+    assert got.shape == y.shape
+    np.testing.assert_allclose(got, y, rtol=1e-3, atol=5e-4)
+    plain = type(ext)(type(ext.config).from_dict({**ext.config.to_dict(), "htk_compat": False})).extract(x, 16000)
+    if c["feature"] == "fbank" and k["use_energy"]:
+        assert np.array_equal(got[:, :-1], plain[:, 1:]) and np.array_equal(got[:, -1], plain[:, 0])  # a pure column move
+    elif c["feature"] == "fbank":
+        assert np.array_equal(got, plain)
 
 
 @pytest.mark.gpu
