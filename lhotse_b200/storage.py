@@ -294,6 +294,14 @@ def compute_and_store_features_fused(
     failure = []  # first exception of a helper thread, re-raised by the caller
     rings = queue.Queue()
     stop = threading.Event()
+    try:
+        cuda_dev = torch.device(str(getattr(extractor.config, "device", "cpu")))
+    except (RuntimeError, TypeError):
+        cuda_dev = torch.device("cpu")
+
+    def _bind_thread():  # a new thread starts on device 0: pinned allocations / event waits must use this rank's GPU
+        if cuda_dev.type == "cuda" and torch.cuda.is_available():
+            torch.cuda.set_device(cuda_dev)
 
     def _staged_batches():  # stage 1: sampler + PCM staging (or the reference's audio loading when the cuts are not plain PCM16 WAV)
         for batch in sampler:
@@ -361,6 +369,7 @@ def compute_and_store_features_fused(
 
             def _reader():
                 try:
+                    _bind_thread()
                     for item in _staged_batches():
                         staged_q.put(item)
                 except BaseException as e:  # noqa: BLE001 - handed to the caller
@@ -370,6 +379,7 @@ def compute_and_store_features_fused(
 
             def _writer_loop():
                 try:
+                    _bind_thread()
                     while True:
                         item = store_q.get()
                         if item is None:
