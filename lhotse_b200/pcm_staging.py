@@ -39,34 +39,64 @@ class NotPcm16Wav(ValueError):
 class _FdCache:
     """A few read-only descriptors kept open across cuts (a corpus job reads thousands of cuts out of the same recordings:
     one open + close per cut costs as much as the read itself).  Reads use `os.preadv`, which carries its own offset, so
-    threads share a descriptor; an entry is dropped when the file's (size, mtime) no longer match."""
+    threads share a descriptor.  A descriptor is only ever closed when no read is using it: `acquire` / `release` count the
+    readers, and an entry that is evicted (capacity) or superseded (the file's size / mtime changed) while in use is closed
+    by its last reader — a closed descriptor number can be handed out again by the OS to ANOTHER file, so closing under a
+    concurrent `preadv` would not fail loudly, it would read the wrong audio."""
+
+    class _Entry:
+        __slots__ = ("fd", "stamp", "users", "dead")
+
+        def __init__(self, fd, stamp):
+            self.fd, self.stamp, self.users, self.dead = fd, stamp, 0, False
 
     def __init__(self, capacity: int = 64):
         self._lock = threading.Lock()
-        self._fds: "OrderedDict[str, Tuple[int, Tuple[int, int]]]" = OrderedDict()
+        self._fds: "OrderedDict[str, _FdCache._Entry]" = OrderedDict()
         self._capacity = capacity
 
-    def get(self, path: str, stamp: Tuple[int, int]) -> int:
+    def _retire(self, ent) -> None:  # lock held
+        ent.dead = True
+        if ent.users == 0:
+            os.close(ent.fd)
+
+    def acquire(self, path: str, stamp: Tuple[int, int]) -> "_FdCache._Entry":
         with self._lock:
             ent = self._fds.get(path)
-            if ent is not None and ent[1] == stamp:
-                self._fds.move_to_end(path)
-                return ent[0]
-            if ent is not None:
-                os.close(ent[0])
+            if ent is not None and ent.stamp != stamp:  # the file was replaced: a new descriptor, the old one goes when idle
                 del self._fds[path]
-            fd = os.open(path, os.O_RDONLY)
-            self._fds[path] = (fd, stamp)
-            while len(self._fds) > self._capacity:
-                _, (old, _) = self._fds.popitem(last=False)
-                os.close(old)
-            return fd
+                self._retire(ent)
+                ent = None
+            if ent is None:
+                ent = self._fds[path] = _FdCache._Entry(os.open(path, os.O_RDONLY), stamp)
+                if len(self._fds) > self._capacity:
+                    for key in list(self._fds):
+                        if len(self._fds) <= self._capacity:
+                            break
+                        old = self._fds[key]
+                        if old is not ent and old.users == 0:  # entries in use stay; the cache may exceed its capacity for a while
+                            del self._fds[key]
+                            self._retire(old)
+            else:
+                self._fds.move_to_end(path)
+            ent.users += 1
+            return ent
+
+    def release(self, ent) -> None:
+        with self._lock:
+            ent.users -= 1
+            if ent.dead and ent.users == 0:
+                os.close(ent.fd)
 
     def clear(self) -> None:
         with self._lock:
-            for fd, _ in self._fds.values():
-                os.close(fd)
+            for ent in self._fds.values():
+                self._retire(ent)
             self._fds.clear()
+
+    def __len__(self) -> int:
+        with self._lock:
+            return len(self._fds)
 
 
 _FDS = _FdCache()
@@ -162,19 +192,22 @@ class WavPcm16:
         if not (0 <= channel < self.channels):
             raise ValueError(f"{self.path}: channel {channel} of {self.channels}")
         assert dst.dtype == np.int16 and dst.ndim == 1 and dst.flags.c_contiguous
-        fd = _FDS.get(self.path, self.stamp)  # shared descriptor; preadv carries its own offset
         pos = self.data_offset + 2 * self.channels * first_sample
         if self.channels == 1:
             view = memoryview(dst).cast("B")
         else:
             raw = np.empty(self.channels * n, dtype="<i2")
             view = memoryview(raw).cast("B")
-        got = 0
-        while got < len(view):
-            k = os.preadv(fd, [view[got:]], pos + got)
-            if not k:
-                raise IOError(f"{self.path}: short read")
-            got += k
+        ent = _FDS.acquire(self.path, self.stamp)  # shared descriptor, held for the duration of the read; preadv carries its own offset
+        try:
+            got = 0
+            while got < len(view):
+                k = os.preadv(ent.fd, [view[got:]], pos + got)
+                if not k:
+                    raise IOError(f"{self.path}: short read")
+                got += k
+        finally:
+            _FDS.release(ent)
         if self.channels != 1:
             dst[:] = raw.reshape(n, self.channels)[:, channel]
         return n

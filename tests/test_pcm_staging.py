@@ -315,3 +315,53 @@ def test_gpu_large_list_routes_take_the_staged_pipelines_and_match():
         assert np.array_equal(ext.extract_batch(tens, 16000).cpu().numpy(), want)
     finally:
         E.STAGING_THREADS = keep
+
+
+def test_descriptor_cache_never_closes_a_descriptor_in_use(tmp_path, monkeypatch):
+    """Many more files than cache slots, read concurrently: every read must return ITS file's samples (a descriptor closed under a
+    concurrent reader could be re-issued by the OS for another file and silently deliver the wrong audio), replaced files are
+    re-opened, and nothing leaks."""
+    import threading
+
+    import lhotse_b200.pcm_staging as ps
+
+    monkeypatch.setattr(ps, "_FDS", ps._FdCache(capacity=3))
+    n_files, n = 24, 4000
+    paths = []
+    for i in range(n_files):
+        p = str(tmp_path / f"f{i}.wav")
+        _write_wav(p, np.full(n, i + 1, dtype=np.int16), 16000)
+        paths.append(p)
+    headers = [WavPcm16.open_cached(p) for p in paths]
+    errors = []
+
+    def worker(seed):
+        rs = np.random.RandomState(seed)
+        buf = np.empty(512, dtype=np.int16)
+        try:
+            for _ in range(400):
+                i = int(rs.randint(n_files))
+                first = int(rs.randint(0, n - 512))
+                headers[i].read_into(buf, first)
+                if not np.all(buf == i + 1):
+                    errors.append((i, int(buf[0])))
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    assert len(ps._FDS) <= 3 + 8
+    # a replaced file (new size / mtime) gets a fresh header and a fresh descriptor
+    _write_wav(paths[0], np.full(n + 100, 77, dtype=np.int16), 16000)
+    h = WavPcm16.open_cached(paths[0])
+    assert h.num_samples == n + 100
+    buf = np.empty(100, dtype=np.int16)
+    h.read_into(buf, n)
+    assert np.all(buf == 77)
+    ps._FDS.clear()
+    assert len(ps._FDS) == 0
