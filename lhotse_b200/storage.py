@@ -294,14 +294,17 @@ def compute_and_store_features_fused(
     failure = []  # first exception of a helper thread, re-raised by the caller
     rings = queue.Queue()
     stop = threading.Event()
+    cuda_index = None  # the GPU this call works on, resolved in the calling thread ("cuda" without an index = its current device)
     try:
-        cuda_dev = torch.device(str(getattr(extractor.config, "device", "cpu")))
-    except (RuntimeError, TypeError):
-        cuda_dev = torch.device("cpu")
+        dev = torch.device(str(getattr(getattr(extractor, "config", None), "device", "cpu")))
+        if dev.type == "cuda" and torch.cuda.is_available():
+            cuda_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    except (RuntimeError, TypeError, ValueError):
+        cuda_index = None
 
     def _bind_thread():  # a new thread starts on device 0: pinned allocations / event waits must use this rank's GPU
-        if cuda_dev.type == "cuda" and torch.cuda.is_available():
-            torch.cuda.set_device(cuda_dev)
+        if cuda_index is not None:
+            torch.cuda.set_device(cuda_index)
 
     def _staged_batches():  # stage 1: sampler + PCM staging (or the reference's audio loading when the cuts are not plain PCM16 WAV)
         for batch in sampler:

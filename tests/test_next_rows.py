@@ -247,6 +247,46 @@ def test_fused_store_manifest_lines_pipeline_and_failures(env, tmp_path, monkeyp
         assert all(c.load_features().shape == (c.num_frames, 80) for c in done)
 
 
+def test_fused_store_helper_threads_bind_the_callers_gpu(env, monkeypatch):
+    """The reader / writer threads of the pipelined store select the GPU the extractor works on — resolved in the calling thread,
+    because the default config says "cuda" without an index and `torch.cuda.set_device` refuses an index-less device."""
+    import threading
+
+    from helpers import attach_oracle_engine
+
+    from lhotse_b200.storage import compute_and_store_features_fused
+
+    cuts, lb_ex, root = env
+    for device, current, want in (("cuda", 3, 3), ("cuda:5", 3, 5), ("cpu", 3, None)):
+        ext = attach_oracle_engine(lb_ex.B200Fbank())
+        ext.config.device = device
+        calls = []
+
+        class _Cuda:  # what storage.py sees as torch.cuda (the rest of the process keeps the real, GPU-less torch)
+            is_available = staticmethod(lambda: True)
+            current_device = staticmethod(lambda: current)
+            set_device = staticmethod(lambda d: calls.append((threading.current_thread().name, d)))
+
+        class _Torch:
+            cuda = _Cuda
+
+            def __getattr__(self, name):
+                return getattr(torch, name)
+
+        import lhotse_b200.storage as st
+
+        monkeypatch.setattr(st, "torch", _Torch())
+        monkeypatch.setenv("B200FEAT_STORE_PIPELINE", "1")
+        out = compute_and_store_features_fused(cuts, ext, root / f"bind_{device.replace(':', '_')}", batch_duration=4.0, num_workers=0,
+                                               overwrite=True, pcm16_fast_path=False)
+        assert len(list(out)) == len(list(cuts))
+        if want is None:
+            assert calls == []
+        else:
+            assert sorted(calls) == [("b200feat-reader", want), ("b200feat-writer", want)]
+        monkeypatch.undo()
+
+
 def test_fused_on_the_fly_mixed_sampling_rates_and_family_adapters(env, tmp_path):
     """`use_batch_extract=False` (reference: sequential `extract` so that sampling rates may differ, input_strategies.py:447-459):
     here one padded extraction per sampling rate, through an extractor that takes the rate per call (torchaudio family)."""
