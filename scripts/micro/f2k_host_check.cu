@@ -90,6 +90,41 @@ int main(int argc, char **argv) {
   printf("mel items: piece %d taps, %d items in %d rounds, %d weight rows (whole-filter rounds: %d rows), simulated wavefronts %ld, "
          "reach %d; worst relative error %.3g, %d bad\n", mi.piece, mi.items, mi.rounds, mi.rows, mo.rows, mi.cost, mi.max_reach, mworst, mbad);
 
+  // ---- whole-filter rounds (fast512 / fast256 / fast400 epilogues, pack_mel_rounds) with the over-read clamp: a short filter at the top
+  // of the band that shares its round with a wide one must start earlier (zero weights in front) instead of reading past `limit`
+  int rbad = 0;
+  {
+    const int K5 = 257, M5 = 40, limit = 260;
+    std::vector<float> b5((size_t)K5 * M5, 0.f);
+    std::vector<double> e5(M5 + 2);
+    for (int m = 0; m < M5 + 2; ++m) e5[m] = 2.0 + 240.0 * (exp(2.2 * m / (M5 + 1)) - 1.0) / (exp(2.2) - 1.0);
+    e5[M5] = 250.0; e5[M5 + 1] = 254.0;  // squeeze the last filter: ~8 taps next to ~30-tap neighbours (what VTLN 0.9 does to a 40-filter bank)
+    for (int m = 0; m < M5; ++m)
+      for (int k = 0; k < K5; ++k) {
+        const double up = (k - e5[m]) / (e5[m + 1] - e5[m]), dn = (e5[m + 2] - k) / (e5[m + 2] - e5[m + 1]);
+        const double w = fmin(up, dn);
+        if (w > 0) b5[(size_t)k * M5 + m] = (float)w;
+      }
+    const MelRounds free_ = pack_mel_rounds(b5, K5, M5, 0.25f, 16, 4), clamped = pack_mel_rounds(b5, K5, M5, 0.25f, 16, 4, limit);
+    std::vector<float> Pz(limit + 64, 0.f);
+    for (int k = 0; k < K5; ++k) Pz[k] = 1.0f + 0.37f * (float)((k * 7919) % 101);
+    for (int j = 0; j < clamped.rounds; ++j)
+      for (int l = 0; l < 16; ++l) {
+        const int m = l + 16 * j;
+        if (m >= M5) continue;
+        float acc = 0.f;
+        const float *pp = Pz.data() + clamped.rstart[j * 16 + l];
+        const float *wp = clamped.wdense.data() + (size_t)clamped.rrow[j] * 16 + l * 4;  // [row / 4][lane][4]
+        for (int i = 0; i < clamped.rlen[j]; i += 4, pp += 4, wp += 64)
+          acc = fmaf(pp[3], wp[3], fmaf(pp[2], wp[2], fmaf(pp[1], wp[1], fmaf(pp[0], wp[0], acc))));
+        double want = 0.0;
+        for (int k = 0; k < K5; ++k) want += 0.25 * (double)b5[(size_t)k * M5 + m] * (double)Pz[k];
+        if (!(fabs(acc - want) <= 1e-5 * fabs(want) + 1e-6)) { if (rbad < 10) printf("clamped rounds, filter %d: got %.9g want %.9g\n", m, acc, want); ++rbad; }
+      }
+    if (!(free_.max_reach > limit) || clamped.max_reach > limit) { printf("clamp: reach %d -> %d (limit %d)\n", free_.max_reach, clamped.max_reach, limit); ++rbad; }
+    printf("whole-filter rounds: reach %d without the clamp, %d with it (limit %d), %d bad\n", free_.max_reach, clamped.max_reach, limit, rbad);
+  }
+
   // ---- the N = 1024 stages (fast1024.cuh): 512-point complex FFT as 16 x 8 x 4 + the same in-lane split with Q = 128
   int wbad = 0;
   {
@@ -131,5 +166,5 @@ int main(int argc, char **argv) {
     }
     printf("fast1024 stages L=%d: worst relative error %.3g over 513 bins, %d bad\n", L1, w1, wbad);
   }
-  return (bad || mbad || wbad) ? 1 : 0;
+  return (bad || mbad || wbad || rbad) ? 1 : 0;
 }

@@ -139,3 +139,25 @@ def test_world2_cutset_level_sharded_store():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert [r[1] for r in res] == [8, 8] and res[0][2] == 0.0  # 4 cuts per rank, corpus order restored, archive bit-exact
+
+
+def test_more_local_ranks_than_gpus_maps_round_robin_and_picks_gloo(monkeypatch):
+    """`dist.init_distributed` for the host-bound store job: with more local ranks than GPUs, local rank r works on GPU r mod #GPUs and
+    the job-level collectives use gloo (NCCL refuses two ranks on one device); one rank per GPU keeps NCCL."""
+    import torch
+
+    import lhotse_b200.dist as lbd
+
+    picked = []
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 4)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(lbd.dist, "is_initialized", lambda: False)
+    monkeypatch.setattr(lbd.dist, "init_process_group", lambda backend, rank, world_size, **kw: picked.append((backend, rank, world_size, sorted(kw))))
+    for rank, world, local, lws, want_dev, want_backend in ((5, 8, 5, 8, 1, "gloo"), (3, 4, 3, 4, 3, "nccl"), (9, 16, 1, 8, 1, "gloo"), (0, 1, 0, 1, 0, None)):
+        for k, v in (("RANK", rank), ("WORLD_SIZE", world), ("LOCAL_RANK", local), ("LOCAL_WORLD_SIZE", lws)):
+            monkeypatch.setenv(k, str(v))
+        picked.clear()
+        r, w, dev = lbd.init_distributed()
+        assert (r, w, dev) == (rank, world, want_dev)
+        assert (picked[0][0] if picked else None) == want_backend

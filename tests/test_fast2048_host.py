@@ -1,6 +1,7 @@
-"""The FFT stages and the mel work-item packing of csrc/fast2048.cuh are `__host__ __device__` / host code: this test compiles
-scripts/micro/f2k_host_check.cu (host side only is executed) and runs the 32 emulated lanes against a float64 DFT and a dense
-(K x M) mel product — the index arithmetic of the kernel is checked without a GPU."""
+"""The FFT stages of csrc/fast2048.cuh and csrc/fast1024.cuh are `__host__ __device__`, the mel packers (balanced 12-tap work items;
+whole-filter rounds with their over-read clamp) are host code: this test compiles scripts/micro/f2k_host_check.cu (only its host side
+is executed) and runs the 32 emulated lanes against a float64 DFT and the packers against a dense (K x M) mel product — the index
+arithmetic of the kernels is checked without a GPU."""
 import os
 import shutil
 import subprocess
